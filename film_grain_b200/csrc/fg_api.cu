@@ -1,0 +1,481 @@
+// fg_api.cu -- C ABI (include/fg.h) over the sm_100a kernels.  Host-side plumbing only:
+// validation, device buffer pools, uploads/downloads, launches, error mapping.
+//
+// There is no CPU fallback anywhere in this file: every render either runs the CUDA
+// kernels or returns an error code.
+#include "../../include/fg.h"
+
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "fg_ctx.cuh"
+#include "fg_kernels.cuh"
+#include "fg_tile.cuh"
+#include "fg_color.cuh"
+#include "fg_zig_tables.h"
+#include <algorithm>
+
+using namespace fg;
+
+namespace {
+
+float uniform_scale(float low, float high) { // rand 0.8.5 UniformFloat<f32>::new
+    uint32_t mr = (0xFFFFFFFFu >> 9) | 0x3F800000u;
+    float max_rand;
+    std::memcpy(&max_rand, &mr, 4);
+    max_rand = max_rand - 1.0f;
+    float scale = high - low;
+    for (;;) {
+        volatile float t = scale * max_rand;
+        volatile float u = t + low;
+        if (!(u >= high)) break;
+        uint32_t b;
+        std::memcpy(&b, &scale, 4);
+        b -= 1;
+        std::memcpy(&scale, &b, 4);
+    }
+    return scale;
+}
+
+int validate(fg_ctx* ctx, const fg_params* p) {
+    if (!p) return set_err(ctx, FG_ERR_INVALID, "params is NULL");
+    if (p->struct_size != sizeof(fg_params))
+        return set_err(ctx, FG_ERR_INVALID, "fg_params.struct_size does not match this library (ABI drift)");
+    if (p->in_w == 0 || p->in_h == 0) return set_err(ctx, FG_ERR_INVALID, "input image is empty");
+    if (p->out_w == 0 || p->out_h == 0) return set_err(ctx, FG_ERR_INVALID, "output dimensions must be positive");
+    if (p->in_w > (1u << 30) || p->in_h > (1u << 30) || p->out_w > (1u << 30) || p->out_h > (1u << 30))
+        return set_err(ctx, FG_ERR_INVALID, "image dimensions too large");
+    if (p->n_samples == 0) return set_err(ctx, FG_ERR_INVALID, "n_samples must be >= 1");
+    if (!(std::isfinite(p->zoom) && p->zoom > 0.0f)) return set_err(ctx, FG_ERR_INVALID, "zoom must be finite and > 0");
+    if (!(std::isfinite(p->delta) && p->delta > 0.0f)) return set_err(ctx, FG_ERR_INVALID, "delta must be finite and > 0");
+    if (!(std::isfinite(p->rm) && p->rm > 0.0f)) return set_err(ctx, FG_ERR_INVALID, "rm must be finite and > 0");
+    if (!std::isfinite(p->radius_mean)) return set_err(ctx, FG_ERR_INVALID, "radius_mean must be finite");
+    if (p->dist_kind > FG_DIST_LOGNORM) return set_err(ctx, FG_ERR_INVALID, "unknown dist_kind");
+    if (p->dist_kind == FG_DIST_LOGNORM && p->has_log &&
+        !(std::isfinite(p->radius_log_mu) && std::isfinite(p->radius_log_sigma) && p->radius_log_sigma >= 0.0))
+        return set_err(ctx, FG_ERR_INVALID, "log-normal parameters must be finite, sigma >= 0");
+    if (p->row_end != 0 || p->row_begin != 0) {
+        if (p->row_begin >= p->row_end || p->row_end > p->out_h)
+            return set_err(ctx, FG_ERR_INVALID, "row band must satisfy row_begin < row_end <= out_h");
+    }
+    if (p->path > FG_PATH_TILED) return set_err(ctx, FG_ERR_INVALID, "unknown path");
+    return FG_OK;
+}
+
+RenderConsts make_consts(const fg_params* p, const float* offsets_host) {
+    RenderConsts c{};
+    c.seed_cell = p->seed ^ 0xA24B1C30BEBCCF59ULL;
+    c.seed_pixel = p->seed ^ 0x6935FA5C55F65F1BULL;
+    c.seeding = p->seeding;
+    c.in_w = (int)p->in_w; c.in_h = (int)p->in_h; c.out_w = (int)p->out_w; c.out_h = (int)p->out_h;
+    c.n = p->n_samples;
+    c.zoom = p->zoom;
+    c.inv_zoom = 1.0f / p->zoom;
+    c.delta = p->delta;
+    c.uscale_cell = uniform_scale(0.0f, p->delta);
+    c.uscale_unit = uniform_scale(0.0f, 1.0f);
+    c.inv_samples = 1.0f / (float)(p->n_samples < 1 ? 1 : p->n_samples);
+    c.rad.lognorm = (p->dist_kind == FG_DIST_LOGNORM && p->has_log) ? 1u : 0u;
+    c.rad.mean_linear = p->radius_mean;
+    c.rad.rm = p->rm;
+    c.rad.mu = p->radius_log_mu;
+    c.rad.sigma = p->radius_log_sigma;
+    if (p->row_begin == 0 && p->row_end == 0) { c.row_begin = 0; c.row_end = (int)p->out_h; }
+    else { c.row_begin = (int)p->row_begin; c.row_end = (int)p->row_end; }
+    float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+    for (uint32_t k = 0; k < p->n_samples; ++k) {
+        float ox = offsets_host[2 * k], oy = offsets_host[2 * k + 1];
+        mnx = fminf(mnx, ox); mxx = fmaxf(mxx, ox); mny = fminf(mny, oy); mxy = fmaxf(mxy, oy);
+    }
+    c.off_min_x = mnx; c.off_max_x = mxx; c.off_min_y = mny; c.off_max_y = mxy;
+    return c;
+}
+
+int check_offsets(fg_ctx* ctx, const fg_params* p, const float* offsets_host) {
+    for (uint32_t k = 0; k < 2 * p->n_samples; ++k)
+        if (!std::isfinite(offsets_host[k])) return set_err(ctx, FG_ERR_INVALID, "offsets must be finite");
+    return FG_OK;
+}
+
+int init_tables(fg_ctx* ctx) {
+    if (ctx->tables_ready) return FG_OK;
+    FG_CUDA(ctx, cudaMemcpyToSymbolAsync(kZigX, FG_ZIG_NORM_X_INIT, sizeof(double) * 257, 0, cudaMemcpyHostToDevice, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyToSymbolAsync(kZigF, FG_ZIG_NORM_F_INIT, sizeof(double) * 257, 0, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->tables_ready = true;
+    return FG_OK;
+}
+
+struct ToU64 {
+    __host__ __device__ uint64_t operator()(uint32_t v) const { return (uint64_t)v; }
+};
+
+__global__ void k_total(const uint32_t* counts, const uint64_t* excl, size_t n, uint64_t* total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *total = n ? excl[n - 1] + counts[n - 1] : 0;
+}
+
+// ---- pixel-wise on device-resident planes ---------------------------------------------
+int pixelwise_device(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
+                     const float* d_offsets, float* d_out) {
+    const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
+    const int band_rows = c.row_end - c.row_begin;
+    uint32_t path = p->path;
+    if (path == FG_PATH_AUTO) path = FG_PATH_TILED;
+    if (path == FG_PATH_TILED) {
+        int rc = tile_render(ctx, p, c, n_planes, d_lambda, d_offsets, d_out);
+        if (rc != 1) return rc; // 1 = "tiled path not applicable, use direct"
+    }
+    dim3 grid((p->out_w + 31) / 32, (band_rows + 7) / 8, n_planes), block(32, 8);
+    k_pixelwise_direct<<<grid, block, 0, ctx->stream>>>(d_lambda, in_stride, (const float2*)d_offsets, d_out, out_stride, c);
+    ctx->stats.launches += 1;
+    FG_CUDA(ctx, cudaGetLastError());
+    return FG_OK;
+}
+
+// ---- grain-wise on a device-resident plane ----------------------------------------------
+int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, const float* d_lambda,
+                           const float* d_offsets, float* d_out) {
+    // input rows whose grains can reach the output band (all rows for a full-plane render)
+    int iy0 = 0, iy1 = (int)p->in_h;
+    if (c.row_begin > 0 || c.row_end < (int)p->out_h) {
+        const double reach = (double)p->rm * p->zoom + 2.0;
+        double lo = ((double)c.row_begin - reach - (double)c.off_max_y) / p->zoom - 2.0;
+        double hi = ((double)c.row_end + reach - (double)c.off_min_y) / p->zoom + 2.0;
+        iy0 = lo > 0 ? (int)lo : 0;
+        iy1 = hi < (double)p->in_h ? (int)hi : (int)p->in_h;
+        if (iy1 < iy0) iy1 = iy0;
+    }
+    const size_t npix_in = (size_t)(iy1 - iy0) * p->in_w;
+    const uint32_t lanes32 = (p->n_samples + 31) / 32;
+    const size_t band_pix = (size_t)(c.row_end - c.row_begin) * p->out_w;
+    int rc;
+    if ((rc = ensure(ctx, ctx->bits, band_pix * lanes32 * sizeof(uint32_t)))) return rc;
+    if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+    FG_CUDA(ctx, cudaMemsetAsync(ctx->bits.p, 0, band_pix * lanes32 * sizeof(uint32_t), ctx->stream));
+    uint64_t* d_total = (uint64_t*)ctx->misc.p;
+    uint64_t total = 0;
+    if (npix_in > 0) {
+        if ((rc = ensure(ctx, ctx->counts, npix_in * sizeof(uint32_t)))) return rc;
+        if ((rc = ensure(ctx, ctx->scan_out, npix_in * sizeof(uint64_t)))) return rc;
+        const unsigned blocks = (unsigned)((npix_in + 255) / 256);
+        k_gw_count<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (uint32_t*)ctx->counts.p, c);
+        FG_CUDA(ctx, cudaGetLastError());
+        cub::TransformInputIterator<uint64_t, ToU64, const uint32_t*> it((const uint32_t*)ctx->counts.p, ToU64());
+        size_t tmp_bytes = 0;
+        FG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, it, (uint64_t*)ctx->scan_out.p, npix_in, ctx->stream));
+        if ((rc = ensure(ctx, ctx->scan_tmp, tmp_bytes))) return rc;
+        FG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, it, (uint64_t*)ctx->scan_out.p, npix_in, ctx->stream));
+        k_total<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->counts.p, (const uint64_t*)ctx->scan_out.p, npix_in, d_total);
+        FG_CUDA(ctx, cudaMemcpyAsync(&total, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stats.launches += 4;
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+        if (total > 0) {
+            if ((rc = ensure(ctx, ctx->grains, total * sizeof(GrainRec)))) return rc;
+            k_gw_fill<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (const uint64_t*)ctx->scan_out.p, (GrainRec*)ctx->grains.p, c);
+            FG_CUDA(ctx, cudaGetLastError());
+            const uint64_t work = total * (uint64_t)p->n_samples;
+            uint64_t want_blocks = (work + 255) / 256;
+            const uint64_t max_blocks = (uint64_t)ctx->sm_count * 32;
+            unsigned sblocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
+            k_gw_splat<<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
+                                                         (uint32_t*)ctx->bits.p, lanes32, c);
+            FG_CUDA(ctx, cudaGetLastError());
+            ctx->stats.launches += 2;
+        }
+    }
+    k_gw_reduce<<<(unsigned)((band_pix + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->bits.p, lanes32, d_out, c);
+    FG_CUDA(ctx, cudaGetLastError());
+    ctx->stats.launches += 1;
+    return FG_OK;
+}
+
+int render_planes_device_locked(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int algo, int n_planes,
+                                const float* d_lambda, const float* d_offsets, float* d_out) {
+    int rc = init_tables(ctx);
+    if (rc) return rc;
+    if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    if (algo == FG_ALGO_PIXEL) return pixelwise_device(ctx, p, c, n_planes, d_lambda, d_offsets, d_out);
+    const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
+    for (int pl = 0; pl < n_planes; ++pl) {
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+        rc = grainwise_device_plane(ctx, p, c, d_lambda + in_stride * pl, d_offsets, d_out + out_stride * pl);
+        if (rc) return rc;
+    }
+    return FG_OK;
+}
+
+int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
+                       const float* offsets, float* const* out) {
+    if (!ctx) return FG_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedDevice dev(ctx->device);
+    ctx->err.clear();
+    ctx->stats = fg_stats{};
+    ctx->fb_pending = false;
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    if (algo != FG_ALGO_PIXEL && algo != FG_ALGO_GRAIN) return set_err(ctx, FG_ERR_INVALID, "algo must be FG_ALGO_PIXEL or FG_ALGO_GRAIN");
+    if (n_planes < 1 || n_planes > 16) return set_err(ctx, FG_ERR_INVALID, "n_planes must be in 1..16");
+    if (!lambda || !offsets || !out) return set_err(ctx, FG_ERR_INVALID, "NULL buffer");
+    for (int pl = 0; pl < n_planes; ++pl)
+        if (!lambda[pl] || !out[pl]) return set_err(ctx, FG_ERR_INVALID, "NULL plane pointer");
+    if ((rc = check_offsets(ctx, p, offsets))) return rc;
+    RenderConsts c = make_consts(p, offsets);
+    const size_t in_elems = (size_t)p->in_w * p->in_h, out_elems = (size_t)p->out_w * p->out_h;
+    if ((rc = ensure(ctx, ctx->lambda, in_elems * n_planes * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->out, out_elems * n_planes * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->offsets, (size_t)p->n_samples * 2 * sizeof(float)))) return rc;
+    cudaStream_t s = ctx->stream;
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+    for (int pl = 0; pl < n_planes; ++pl)
+        FG_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lambda.p + in_elems * pl, lambda[pl], in_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    FG_CUDA(ctx, cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)p->n_samples * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+    rc = render_planes_device_locked(ctx, p, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, (float*)ctx->out.p);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+    const size_t band_off = (size_t)c.row_begin * p->out_w, band_elems = (size_t)(c.row_end - c.row_begin) * p->out_w;
+    for (int pl = 0; pl < n_planes; ++pl)
+        FG_CUDA(ctx, cudaMemcpyAsync(out[pl] + band_off, (float*)ctx->out.p + out_elems * pl + band_off, band_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+    FG_CUDA(ctx, cudaStreamSynchronize(s));
+    cudaEventElapsedTime(&ctx->stats.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->stats.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->stats.h2d_bytes = (in_elems * n_planes + (size_t)p->n_samples * 2) * sizeof(float);
+    ctx->stats.d2h_bytes = band_elems * n_planes * sizeof(float);
+    if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    return FG_OK;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------- ABI
+extern "C" {
+
+int fg_abi_version(void) { return FG_ABI_VERSION; }
+
+int fg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* fg_error_string(int code) {
+    switch (code) {
+    case FG_OK: return "ok";
+    case FG_ERR_INVALID: return "invalid argument";
+    case FG_ERR_OOM: return "out of device memory";
+    case FG_ERR_CUDA_STICKY: return "unrecoverable CUDA error (drop the context)";
+    case FG_ERR_NO_DEVICE: return "no usable CUDA device";
+    case FG_ERR_CANCELLED: return "cancelled";
+    case FG_ERR_CUDA: return "CUDA error";
+    default: return "unknown error";
+    }
+}
+
+int fg_context_create(fg_ctx** out, int device) {
+    if (!out) return FG_ERR_INVALID;
+    *out = nullptr;
+    int n = fg_device_count();
+    if (n <= 0 || device < 0 || device >= n) return FG_ERR_NO_DEVICE;
+    fg_ctx* ctx = new (std::nothrow) fg_ctx();
+    if (!ctx) return FG_ERR_OOM;
+    ctx->device = device;
+    ScopedDevice dev(device);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        cudaGetLastError();
+        delete ctx;
+        return FG_ERR_NO_DEVICE; // kernels are sm_100a only
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return FG_ERR_CUDA_STICKY;
+    }
+    for (auto& e : ctx->ev) cudaEventCreate(&e);
+    int rc = tile_setup(ctx);
+    if (rc) { fg_context_destroy(ctx); return rc; }
+    *out = ctx;
+    return FG_OK;
+}
+
+void fg_context_destroy(fg_ctx* ctx) {
+    if (!ctx) return;
+    {
+        ScopedDevice dev(ctx->device);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+        for (DevBuf* b : {&ctx->lambda, &ctx->out, &ctx->offsets, &ctx->bits, &ctx->counts, &ctx->scan_out, &ctx->scan_tmp,
+                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut})
+            release(*b);
+        if (ctx->pin_in.p) cudaFreeHost(ctx->pin_in.p);
+        if (ctx->pin_out.p) cudaFreeHost(ctx->pin_out.p);
+        for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        cudaGetLastError();
+    }
+    delete ctx;
+}
+
+const char* fg_last_error(const fg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void fg_set_cancel_flag(fg_ctx* ctx, const volatile int* flag) { if (ctx) ctx->cancel = flag; }
+void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
+    if (!ctx || !out) return;
+    *out = ctx->stats;
+    if (ctx->fb_pending) out->tiles_fallback = ctx->fb_count_host; // meaningful once the stream is synchronised
+}
+uint64_t fg_context_stream(const fg_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+
+int fg_context_synchronize(fg_ctx* ctx) {
+    if (!ctx) return FG_ERR_INVALID;
+    ScopedDevice dev(ctx->device);
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return FG_OK;
+}
+
+int fg_render_pixelwise(fg_ctx* ctx, const fg_params* p, const float* lambda, const float* offsets_input, float* out) {
+    const float* lp[1] = {lambda};
+    float* op[1] = {out};
+    return render_planes_host(ctx, p, FG_ALGO_PIXEL, 1, lp, offsets_input, op);
+}
+
+int fg_render_grainwise(fg_ctx* ctx, const fg_params* p, const float* lambda, const float* offsets, float* out) {
+    const float* lp[1] = {lambda};
+    float* op[1] = {out};
+    return render_planes_host(ctx, p, FG_ALGO_GRAIN, 1, lp, offsets, op);
+}
+
+int fg_render_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
+                     const float* offsets, float* const* out) {
+    return render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out);
+}
+
+int fg_render_planes_device(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* d_lambda,
+                            const float* d_offsets, float* d_out, int stream_sync) {
+    if (!ctx) return FG_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedDevice dev(ctx->device);
+    ctx->err.clear();
+    ctx->stats = fg_stats{};
+    ctx->fb_pending = false;
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    if (algo != FG_ALGO_PIXEL && algo != FG_ALGO_GRAIN) return set_err(ctx, FG_ERR_INVALID, "algo must be FG_ALGO_PIXEL or FG_ALGO_GRAIN");
+    if (n_planes < 1 || n_planes > 16) return set_err(ctx, FG_ERR_INVALID, "n_planes must be in 1..16");
+    if (!d_lambda || !d_offsets || !d_out) return set_err(ctx, FG_ERR_INVALID, "NULL buffer");
+    // the offset extremes size the tile windows: read the (tiny) offset array back once
+    std::vector<float> off((size_t)p->n_samples * 2);
+    FG_CUDA(ctx, cudaMemcpyAsync(off.data(), d_offsets, off.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = check_offsets(ctx, p, off.data()))) return rc;
+    RenderConsts c = make_consts(p, off.data());
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = render_planes_device_locked(ctx, p, c, algo, n_planes, d_lambda, d_offsets, d_out);
+    if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (stream_sync) {
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    }
+    return FG_OK;
+}
+
+int fg_render_rgb8(fg_ctx* ctx, const fg_params* p, int algo, int color_mode, const uint8_t* rgb_in,
+                   const float* offsets, uint8_t* rgb_out) {
+    if (!ctx) return FG_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedDevice dev(ctx->device);
+    ctx->err.clear();
+    ctx->stats = fg_stats{};
+    ctx->fb_pending = false;
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    if (!rgb_in || !offsets || !rgb_out) return set_err(ctx, FG_ERR_INVALID, "NULL buffer");
+    return color_render_host(ctx, p, algo, color_mode, rgb_in, offsets, rgb_out);
+}
+
+int fg_render_rgb8_device(fg_ctx* ctx, const fg_params* p, int algo, int color_mode, const uint8_t* d_rgb_in,
+                          const float* d_offsets, uint8_t* d_rgb_out, int stream_sync) {
+    if (!ctx) return FG_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedDevice dev(ctx->device);
+    ctx->err.clear();
+    ctx->stats = fg_stats{};
+    ctx->fb_pending = false;
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    if (!d_rgb_in || !d_offsets || !d_rgb_out) return set_err(ctx, FG_ERR_INVALID, "NULL buffer");
+    return color_render_device(ctx, p, algo, color_mode, d_rgb_in, d_offsets, d_rgb_out, stream_sync);
+}
+
+int fg_dump_cells(fg_ctx* ctx, const fg_params* p, int stream_kind, const int32_t* ij, const float* lambda_cell,
+                  size_t n, uint32_t cap, uint32_t* q_out, float* grains_out) {
+    if (!ctx) return FG_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedDevice dev(ctx->device);
+    ctx->err.clear();
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    if (stream_kind != FG_STREAM_CELL && stream_kind != FG_STREAM_PIXEL) return set_err(ctx, FG_ERR_INVALID, "unknown stream_kind");
+    if (!ij || !lambda_cell || !q_out || (cap && !grains_out)) return set_err(ctx, FG_ERR_INVALID, "NULL buffer");
+    if (n == 0) return FG_OK;
+    if ((rc = init_tables(ctx))) return rc;
+    float zero2[2] = {0.0f, 0.0f};
+    fg_params pp = *p;
+    pp.n_samples = 1;
+    RenderConsts c = make_consts(&pp, zero2);
+    DevBuf d_ij, d_lam, d_q, d_g;
+    auto cleanup = [&]() { release(d_ij); release(d_lam); release(d_q); release(d_g); };
+    if ((rc = ensure(ctx, d_ij, n * 8)) || (rc = ensure(ctx, d_lam, n * 4)) || (rc = ensure(ctx, d_q, n * 4)) ||
+        (rc = ensure(ctx, d_g, n * (size_t)(cap ? cap : 1) * 12))) { cleanup(); return rc; }
+    cudaStream_t s = ctx->stream;
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_ij.p, ij, n * 8, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_lam.p, lambda_cell, n * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+        (e = cudaMemsetAsync(d_g.p, 0, n * (size_t)(cap ? cap : 1) * 12, s)) != cudaSuccess) { cleanup(); return map_cuda_error(ctx, e, "dump upload"); }
+    k_dump_cells<<<(unsigned)((n + 127) / 128), 128, 0, s>>>((const int2*)d_ij.p, (const float*)d_lam.p, n, cap, stream_kind,
+                                                               (uint32_t*)d_q.p, (float*)d_g.p, c);
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(q_out, d_q.p, n * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess ||
+        (cap && (e = cudaMemcpyAsync(grains_out, d_g.p, n * (size_t)cap * 12, cudaMemcpyDeviceToHost, s)) != cudaSuccess) ||
+        (e = cudaStreamSynchronize(s)) != cudaSuccess) { cleanup(); return map_cuda_error(ctx, e, "dump cells"); }
+    cleanup();
+    return FG_OK;
+}
+
+int fg_measure_issue_peak(fg_ctx* ctx, double out[4]) {
+    if (!ctx || !out) return FG_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedDevice dev(ctx->device);
+    ctx->err.clear();
+    int rc;
+    if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
+    const uint32_t iters = 4096;
+    const unsigned blocks = (unsigned)ctx->sm_count * 2, threads = 1024;
+    const double ops_per_thread[4] = {64.0 * iters, 64.0 * iters, 64.0 * iters, 32.0 * iters};
+    for (int kind = 0; kind < 4; ++kind) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+            switch (kind) {
+            case 0: k_issue_peak<0><<<blocks, threads, 0, ctx->stream>>>(iters, (uint32_t*)ctx->misc.p); break;
+            case 1: k_issue_peak<1><<<blocks, threads, 0, ctx->stream>>>(iters, (uint32_t*)ctx->misc.p); break;
+            case 2: k_issue_peak<2><<<blocks, threads, 0, ctx->stream>>>(iters, (uint32_t*)ctx->misc.p); break;
+            default: k_issue_peak<3><<<blocks, threads, 0, ctx->stream>>>(iters, (uint32_t*)ctx->misc.p); break;
+            }
+            FG_CUDA(ctx, cudaGetLastError());
+            FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+            FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        out[kind] = ops_per_thread[kind] * (double)blocks * threads / (best * 1e-3) / 1e9;
+    }
+    return FG_OK;
+}
+
+} // extern "C"

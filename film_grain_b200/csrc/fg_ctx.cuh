@@ -1,0 +1,120 @@
+// fg_ctx.cuh -- context object and host-side plumbing shared by fg_api.cu, fg_tile.cuh and
+// fg_color.cuh (buffer pools, error mapping).  Host code only.
+#pragma once
+#include "../../include/fg.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+// ----------------------------------------------------------------------------- context
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct HostBuf { // pinned staging
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+} // namespace
+
+struct fg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::mutex mu;
+    std::string err;
+    const volatile int* cancel = nullptr;
+    fg_stats stats{};
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    // pools
+    DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, rgb_in, rgb_out, chroma, lut;
+    HostBuf pin_in, pin_out;
+    bool tables_ready = false;
+    uint32_t fb_count_host = 0; // tiled path: fallback-list length of the last render (valid after a stream sync)
+    bool fb_pending = false;
+};
+
+namespace {
+
+struct ScopedDevice {
+    int prev = -1;
+    explicit ScopedDevice(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~ScopedDevice() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int set_err(fg_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int map_cuda_error(fg_ctx* ctx, cudaError_t e, const char* what) {
+    cudaGetLastError(); // clear non-sticky state
+    std::string msg = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    int code;
+    switch (e) {
+    case cudaErrorMemoryAllocation: code = FG_ERR_OOM; break;
+    case cudaErrorNoDevice:
+    case cudaErrorInvalidDevice:
+    case cudaErrorInsufficientDriver: code = FG_ERR_NO_DEVICE; break;
+    case cudaErrorInvalidValue:
+    case cudaErrorInvalidConfiguration:
+    case cudaErrorLaunchOutOfResources: code = FG_ERR_CUDA; break;
+    default: code = FG_ERR_CUDA_STICKY; break; // illegal address, launch failure, ECC, ...
+    }
+    return set_err(ctx, code, msg);
+}
+
+#define FG_CUDA(ctx, expr)                                              \
+    do {                                                                \
+        cudaError_t e__ = (expr);                                       \
+        if (e__ != cudaSuccess) return map_cuda_error((ctx), e__, #expr); \
+    } while (0)
+
+int ensure(fg_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return FG_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 8 + 256; // a little headroom so sweeps do not realloc every call
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        e = cudaMalloc(&b.p, bytes);
+        want = bytes;
+    }
+    if (e != cudaSuccess) { b.p = nullptr; return map_cuda_error(ctx, e, "cudaMalloc"); }
+    b.cap = want;
+    return FG_OK;
+}
+
+int ensure_pinned(fg_ctx* ctx, HostBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return FG_OK;
+    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    cudaError_t e = cudaMallocHost(&b.p, bytes);
+    if (e != cudaSuccess) { b.p = nullptr; return map_cuda_error(ctx, e, "cudaMallocHost"); }
+    b.cap = bytes;
+    return FG_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+}
+
+bool cancelled(const fg_ctx* ctx) { return ctx->cancel && *ctx->cancel != 0; }
+
+} // namespace

@@ -1,0 +1,527 @@
+// fg_tile.cuh -- the pixel-wise fast path: one CTA per output STRIP SEGMENT.
+//
+// Reference semantics (src/pixelwise.rs:11-106): pixel = (1/N) * #{k : some grain of the cells
+// within rm of the k-th shifted sample point covers it}.  The reference regenerates every cell
+// for every sample of every pixel; here each CTA owns a strip of 32 output columns x SEG rows and
+//
+//   * generates every Boolean-model cell its window touches exactly ONCE into shared memory
+//     (bit-identical RNG chain: fg_rng.cuh), sliding the window down the strip TH pixel rows at
+//     a time through a ring of cell rows, so the only regenerated margin is the horizontal one;
+//   * generation is two-phase and compacted: phase A runs the cheap first-draw test on all
+//     cells (4 of the 8 PCG seed words + 1 xoshiro draw + an integer threshold compare that is
+//     exactly `U1 <= exp(-lambda')`); only the non-empty cells (~27% at lambda'=1/pi) go through
+//     the dense phase B (full seeding, Knuth continuation in f64, positions) -- no lane idles on
+//     an empty cell;
+//   * grains are stored per cell row in cell order (CSR): P[row][i] (u16 ring positions) and
+//     G[pos] = (cx, cy); a sample's candidates in one cell row are one contiguous range;
+//   * evaluation: lane = output column, warp = sample subset; the per-(column,sample) cell range
+//     and the per-(row,sample) cell-row range are computed ONCE (IEEE division, exactly the
+//     reference's expression) and reused across the rows / columns they do not depend on.
+//
+// Anything the fast path cannot hold (lambda' >= 12 -> rejection branch, window or grain ring
+// overflow, log-normal radii, exotic geometry) is appended to a fallback list and rendered by the
+// general direct kernel (fg_kernels.cuh) in the same call: results are identical either way.
+#pragma once
+#include "fg_ctx.cuh"
+#include "fg_kernels.cuh"
+
+namespace fg {
+
+#define FG_THR_EMPTY (1ULL << 53)          // first-draw threshold that no draw exceeds (cell skipped)
+#define FG_THR_GENERAL 0xFFFFFFFFFFFFFFFFULL // cell needs the general path (lambda' >= 12 / non-finite)
+
+// Per input pixel: thr = floor(exp(-lambda') * 2^53), e = exp(-lambda') with lambda' = lambda*delta*delta
+// (src/pixelwise.rs:71-81).  The Knuth loop's first decision `p = U1 > e` with U1 = m * 2^-53
+// (m = next_u64 >> 11) is exactly `m > thr`.
+__global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ lambda, size_t n, float delta,
+                                                     uint64_t* __restrict__ thr, double* __restrict__ ev) {
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (size_t)gridDim.x * 256) {
+        float lam = lambda[t];
+        uint64_t th = FG_THR_EMPTY;
+        double e = 1.0;
+        if (lam > 0.0f) {
+            float expected = __fmul_rn(__fmul_rn(lam, delta), delta);
+            if (expected > 0.0f) {
+                if (expected < 12.0f) {
+                    e = exp(-(double)expected);
+                    th = (uint64_t)(e * 9007199254740992.0);
+                } else {
+                    th = FG_THR_GENERAL;
+                }
+            }
+        } else if (lam != lam) {
+            th = FG_THR_GENERAL;
+        }
+        thr[t] = th;
+        ev[t] = e;
+    }
+}
+
+struct __align__(16) ColInfo { uint64_t h; float sx; int ixc; }; // per cell column: mix3 first half, i*delta, clamped input x
+
+struct TileCfg {
+    int TH, SEG;          // pixel rows per step, rows per segment
+    int CWB, RH, PS;      // cell-column bound, ring rows, P row stride (u16 elements)
+    int R;                // cell rows per generation group
+    int GCAP;             // grain ring capacity (power of two <= 65536)
+    int n_strips, n_segs;
+    uint32_t off_col, off_P, off_G, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, total;
+};
+
+#define FG_TILE_THREADS 512
+#define FG_TILE_WARPS 16
+#define FG_TILE_ITERS 4 // phase-A cells per thread per group: R*(CW+1) <= 2048
+
+__device__ __forceinline__ void push_fallback(TileRef* list, uint32_t* count, uint32_t cap, int x0, int y0, int w,
+                                              int h, int plane) {
+    uint32_t idx = atomicAdd(count, 1u);
+    if (idx < cap) {
+        TileRef t;
+        t.x0 = x0; t.y0 = y0; t.w = w; t.h = h; t.plane = plane;
+        list[idx] = t;
+    }
+}
+
+// floor((v -/+ rm) / delta) exactly as src/pixelwise.rs:55-58
+__device__ __forceinline__ int cell_lo(float v, float rm, float delta) { return floor_i32(__fdiv_rn(__fsub_rn(v, rm), delta)); }
+__device__ __forceinline__ int cell_hi(float v, float rm, float delta) { return floor_i32(__fdiv_rn(__fadd_rn(v, rm), delta)); }
+
+template <int SPWC>
+__global__ void __launch_bounds__(FG_TILE_THREADS, 1)
+k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restrict__ e_planes, size_t in_stride,
+                  const float2* __restrict__ offsets_input, float* __restrict__ out, size_t out_stride,
+                  TileRef* __restrict__ fb_list, uint32_t* __restrict__ fb_count, uint32_t fb_cap, TileCfg cfg,
+                  RenderConsts c) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    ColInfo* colT = (ColInfo*)(smem + cfg.off_col);
+    uint16_t* P = (uint16_t*)(smem + cfg.off_P);
+    float2* G = (float2*)(smem + cfg.off_G);
+    uint16_t* list = (uint16_t*)(smem + cfg.off_list);
+    uint16_t* E = (uint16_t*)(smem + cfg.off_E);
+    uint32_t* cntA = (uint32_t*)(smem + cfg.off_cnt);  // [64] counts, [64..128] exclusive offsets, [128] total
+    uint32_t* wtot = (uint32_t*)(smem + cfg.off_wtot); // [16] warp totals, [16] flag
+    uint32_t* pcount = (uint32_t*)(smem + cfg.off_pcount);
+    float2* wpair = (float2*)(smem + cfg.off_wpair);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int unit = blockIdx.x;
+    const int strip = unit % cfg.n_strips;
+    const int seg = (unit / cfg.n_strips) % cfg.n_segs;
+    const int plane = unit / (cfg.n_strips * cfg.n_segs);
+    const int X0 = strip * 32;
+    const int Y0 = c.row_begin + seg * cfg.SEG;
+    if (X0 >= c.out_w || Y0 >= c.row_end) return;
+    const int X1 = min(X0 + 32, c.out_w) - 1;      // inclusive
+    const int Y1 = min(Y0 + cfg.SEG, c.row_end);   // exclusive
+    const uint64_t* thr = thr_planes + in_stride * plane;
+    const double* ev = e_planes + in_stride * plane;
+    float* outp = out + out_stride * plane;
+    const float rm = c.rad.rm, delta = c.delta;
+    const float r2 = __fmul_rn(c.rad.mean_linear > rm ? rm : c.rad.mean_linear, c.rad.mean_linear > rm ? rm : c.rad.mean_linear);
+    const bool radius_ok = (c.rad.mean_linear > rm ? rm : c.rad.mean_linear) > 0.0f; // radius <= 0: grains never cover
+    const int GM = cfg.GCAP - 1;
+
+    // ---- horizontal cell window of the strip (monotone in x and in the offset) ----
+    const float bx0 = __fmul_rn(__fadd_rn((float)X0, 0.5f), c.inv_zoom);
+    const float bx1 = __fmul_rn(__fadd_rn((float)X1, 0.5f), c.inv_zoom);
+    const int i_lo = cell_lo(__fsub_rn(bx0, c.off_max_x), rm, delta);
+    const int i_hi = cell_hi(__fsub_rn(bx1, c.off_min_x), rm, delta);
+    const long long CWl = (long long)i_hi - (long long)i_lo + 1;
+    if (CWl < 1 || CWl > cfg.CWB) { // uniform
+        if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, Y0, X1 - X0 + 1, Y1 - Y0, plane);
+        return;
+    }
+    const int CW = (int)CWl, CW1 = CW + 1;
+    const int PS = cfg.PS, RH = cfg.RH;
+
+    for (int il = tid; il < CW; il += FG_TILE_THREADS) {
+        ColInfo ci;
+        int i = i_lo + il;
+        ci.h = mix3_col(c.seed_cell, i);
+        ci.sx = __fmul_rn(__int2float_rn(i), delta);
+        long long ix = floor_i64(ci.sx);
+        ci.ixc = (int)(ix < 0 ? 0 : (ix > c.in_w - 1 ? c.in_w - 1 : ix));
+        colT[il] = ci;
+    }
+    for (int p = tid; p < cfg.TH * 32; p += FG_TILE_THREADS) pcount[p] = 0;
+    if (tid == 0) wtot[16] = 0;
+
+    // phase-A cell assignment of this thread: cell c = tid + 512*it -> (r, il), il == CW is the row sentinel
+    int rci[FG_TILE_ITERS];
+#pragma unroll
+    for (int it = 0; it < FG_TILE_ITERS; ++it) {
+        int cc = tid + FG_TILE_THREADS * it;
+        int r = cc / CW1;
+        rci[it] = (r < cfg.R) ? ((r << 16) | (cc - r * CW1)) : -1;
+    }
+
+    // per-thread (column, sample) data: sample point x and its cell-column range [a, b)
+    const int x = X0 + lane;
+    const bool xvalid = x <= X1;
+    const float bx = __fmul_rn(__fadd_rn((float)x, 0.5f), c.inv_zoom);
+    float xg_r[SPWC];
+    uint32_t ip_r[SPWC];
+    const int n_chunks = (int)((c.n + 16 * SPWC - 1) / (16 * SPWC));
+    auto load_xk = [&](int chunk) {
+#pragma unroll
+        for (int s = 0; s < SPWC; ++s) {
+            uint32_t k = (uint32_t)chunk * (16 * SPWC) + s * 16 + warp;
+            float xg = 0.0f;
+            uint32_t ip = 0;
+            if (k < c.n && xvalid) {
+                float2 o = __ldg(offsets_input + k);
+                xg = __fsub_rn(bx, o.x);
+                int i0 = cell_lo(xg, rm, delta), i1 = cell_hi(xg, rm, delta);
+                if (i0 <= i1) ip = (uint32_t)(i0 - i_lo) | ((uint32_t)(i1 - i_lo + 1) << 16);
+            }
+            xg_r[s] = xg;
+            ip_r[s] = ip;
+        }
+    };
+    if (n_chunks == 1) load_xk(0);
+    __syncthreads();
+
+    // ---- ring state (uniform across the CTA) ----
+    uint32_t head = 0;            // absolute grain counter; ring position = head & GM; P holds (u16)head
+    int j_gen = 0, rr_gen = 0;    // next cell row to generate and its ring row
+    int j_lo_prev = 0, rr_lo = 0; // oldest live cell row and its ring row
+    bool first = true;
+
+    for (int ya = Y0; ya < Y1; ya += cfg.TH) {
+        const int yb = min(ya + cfg.TH, Y1) - 1; // inclusive
+        const int th = yb - ya + 1;
+        const float bya = __fmul_rn(__fadd_rn((float)ya, 0.5f), c.inv_zoom);
+        const float byb = __fmul_rn(__fadd_rn((float)yb, 0.5f), c.inv_zoom);
+        const int j_lo = cell_lo(__fsub_rn(bya, c.off_max_y), rm, delta);
+        const int j_hi = cell_hi(__fsub_rn(byb, c.off_min_y), rm, delta);
+        const long long WH = (long long)j_hi - (long long)j_lo + 1;
+        bool fail = (WH < 1 || WH > RH);
+        if (!fail) {
+            if (first) { j_gen = j_lo; rr_gen = 0; rr_lo = 0; first = false; }
+            else {
+                long long adv = (long long)j_lo - j_lo_prev; // >= 0 (monotone in y)
+                if (adv >= RH || j_lo >= j_gen) { j_gen = max(j_gen, j_lo); rr_lo = rr_gen; if (j_gen > j_lo) fail = true; }
+                else { rr_lo += (int)adv; if (rr_lo >= RH) rr_lo -= RH; }
+            }
+            j_lo_prev = j_lo;
+        }
+        if (fail) {
+            if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
+            return;
+        }
+        uint32_t used = (j_lo < j_gen) ? ((head - (uint32_t)P[rr_lo * PS]) & 0xFFFFu) : 0u;
+
+        // =================== generation: cell rows j_gen .. j_hi in groups of R ===================
+        while (j_gen <= j_hi) {
+            const int nr = min(cfg.R, j_hi - j_gen + 1);
+            // ---- phase A: first-draw filter on every cell of the group ----
+            uint32_t masks[FG_TILE_ITERS];
+#pragma unroll
+            for (int it = 0; it < FG_TILE_ITERS; ++it) {
+                bool nonempty = false;
+                const int rc = rci[it];
+                if (rc >= 0 && (rc >> 16) < nr && (rc & 0xFFFF) < CW) {
+                    const int il = rc & 0xFFFF, j = j_gen + (rc >> 16);
+                    const ColInfo ci = colT[il];
+                    const float sy = __fmul_rn(__int2float_rn(j), delta);
+                    long long iy = floor_i64(sy);
+                    iy = iy < 0 ? 0 : (iy > c.in_h - 1 ? c.in_h - 1 : iy);
+                    const uint64_t th64 = __ldg(thr + (size_t)iy * c.in_w + ci.ixc);
+                    const uint64_t h = mix3_row(ci.h, j);
+                    uint64_t s0, s3;
+                    if (c.seeding == 0) { s0 = pcg_word_pair<0>(h); s3 = pcg_word_pair<3>(h); }
+                    else { Xoshiro t; seed_splitmix(t, h); s0 = t.s0; s3 = t.s3; }
+                    const uint64_t m1 = (rotl64(s0 + s3, 23) + s0) >> 11;
+                    if (th64 == FG_THR_GENERAL) wtot[16] = 1;
+                    else nonempty = m1 > th64;
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, nonempty);
+                masks[it] = m;
+                if (lane == 0) cntA[it * 16 + warp] = __popc(m);
+            }
+            __syncthreads();
+            if (warp == 0) { // exclusive scan of the 64 (it, warp) counts
+                uint32_t a = cntA[2 * lane], b = cntA[2 * lane + 1];
+                uint32_t s = a + b, incl = s;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                uint32_t excl = incl - s;
+                cntA[64 + 2 * lane] = excl;
+                cntA[64 + 2 * lane + 1] = excl + a;
+                if (lane == 31) cntA[128] = incl;
+            }
+            __syncthreads();
+            if (wtot[16]) { // a cell of this group needs the general path: hand the rest of the segment over
+                if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
+                return;
+            }
+            const uint32_t M = cntA[128];
+#pragma unroll
+            for (int it = 0; it < FG_TILE_ITERS; ++it) {
+                if ((masks[it] >> lane) & 1u) {
+                    uint32_t pos = cntA[64 + it * 16 + warp] + __popc(masks[it] & lt_mask);
+                    list[pos] = (uint16_t)(((rci[it] >> 16) << 12) | (rci[it] & 0xFFF));
+                }
+            }
+            __syncthreads();
+            // ---- phase B (dense): full seeding, Knuth continuation, positions ----
+            for (uint32_t base = 0; base < M; base += FG_TILE_THREADS) {
+                const uint32_t t = base + tid;
+                uint32_t q = 0;
+                Xoshiro rng;
+                float sx = 0.0f, sy = 0.0f;
+                if (t < M) {
+                    const uint32_t item = list[t];
+                    const int il = item & 0xFFF, j = j_gen + (int)(item >> 12);
+                    const ColInfo ci = colT[il];
+                    sx = ci.sx;
+                    sy = __fmul_rn(__int2float_rn(j), delta);
+                    long long iy = floor_i64(sy);
+                    iy = iy < 0 ? 0 : (iy > c.in_h - 1 ? c.in_h - 1 : iy);
+                    const double e = __ldg(ev + (size_t)iy * c.in_w + ci.ixc);
+                    seed_small_rng(rng, mix3_row(ci.h, j), c.seeding);
+                    double p = standard_f64(rng); // first draw (known > e)
+                    while (p > e) { p = __dmul_rn(p, standard_f64(rng)); ++q; }
+                }
+                // block-wide exclusive scan of q
+                uint32_t incl = q;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                if (lane == 31) wtot[warp] = incl;
+                __syncthreads();
+                uint32_t boff = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < FG_TILE_WARPS; ++w) {
+                    uint32_t v = wtot[w];
+                    if (w < warp) boff += v;
+                    total += v;
+                }
+                if (used + total > (uint32_t)cfg.GCAP) { // uniform: grain ring overflow
+                    if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
+                    return;
+                }
+                if (t < M) {
+                    uint32_t pos = head + boff + (incl - q);
+                    E[t] = (uint16_t)pos;
+                    for (uint32_t g = 0; g < q; ++g) {
+                        float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
+                        float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
+                        G[(pos + g) & GM] = make_float2(cx, cy);
+                    }
+                }
+                head += total;
+                used += total;
+                __syncthreads(); // wtot reuse + E/G visible
+            }
+            if (tid == 0) E[M] = (uint16_t)head;
+            __syncthreads();
+            // ---- P fill: ring position of the first grain at or after each cell ----
+#pragma unroll
+            for (int it = 0; it < FG_TILE_ITERS; ++it) {
+                const int rc = rci[it];
+                if (rc >= 0 && (rc >> 16) < nr) {
+                    uint32_t rank = cntA[64 + it * 16 + warp] + __popc(masks[it] & lt_mask);
+                    int rr = rr_gen + (rc >> 16);
+                    if (rr >= RH) rr -= RH;
+                    P[rr * PS + (rc & 0xFFFF)] = E[rank];
+                }
+            }
+            j_gen += nr;
+            rr_gen += nr;
+            if (rr_gen >= RH) rr_gen -= RH;
+            __syncthreads();
+        }
+
+        // =================== evaluation of pixel rows ya..yb ===================
+        for (int chunk = 0; chunk < n_chunks; ++chunk) {
+            if (n_chunks > 1) load_xk(chunk);
+            // per-(row, sample) data of this warp: sample point y and its cell-row range
+            float2* wp = wpair + warp * (cfg.TH * SPWC);
+            for (int qd = lane; qd < th * SPWC; qd += 32) {
+                const int s = qd / th, yl = qd - s * th;
+                const uint32_t k = (uint32_t)chunk * (16 * SPWC) + s * 16 + warp;
+                float yg = 0.0f;
+                uint32_t jp = 0;
+                if (k < c.n) {
+                    const float by = __fmul_rn(__fadd_rn((float)(ya + yl), 0.5f), c.inv_zoom);
+                    yg = __fsub_rn(by, __ldg(offsets_input + k).y);
+                    const int j0 = cell_lo(yg, rm, delta), j1 = cell_hi(yg, rm, delta);
+                    if (j0 <= j1) {
+                        int rr = rr_lo + (j0 - j_lo);
+                        if (rr >= RH) rr -= RH;
+                        jp = (uint32_t)rr | ((uint32_t)(j1 - j0 + 1) << 16);
+                    }
+                }
+                wp[s * th + yl] = make_float2(yg, __uint_as_float(jp));
+            }
+            __syncwarp();
+            if (xvalid && radius_ok) {
+                for (int yl = 0; yl < th; ++yl) {
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int s = 0; s < SPWC; ++s) {
+                        const float2 pd = wp[s * th + yl];
+                        const uint32_t jp = __float_as_uint(pd.y);
+                        const uint32_t ip = ip_r[s];
+                        const int a = ip & 0xFFFF, b = ip >> 16;
+                        int nrow = (a < b) ? (int)(jp >> 16) : 0;
+                        int rr = jp & 0xFFFF;
+                        const float xg = xg_r[s], yg = pd.x;
+                        bool covered = false;
+                        while (nrow > 0 && !covered) {
+                            const uint16_t* prow = P + rr * PS;
+                            const uint32_t s16 = prow[a], e16 = prow[b];
+                            uint32_t n = (e16 - s16) & 0xFFFFu;
+                            uint32_t idx = s16;
+                            while (n > 0) {
+                                const float2 gr = G[idx & GM];
+                                const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
+                                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= r2) { covered = true; break; }
+                                ++idx; --n;
+                            }
+                            ++rr; if (rr >= RH) rr = 0;
+                            --nrow;
+                        }
+                        cnt += covered ? 1u : 0u;
+                    }
+                    if (cnt) atomicAdd(&pcount[yl * 32 + lane], cnt);
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        for (int p = tid; p < th * 32; p += FG_TILE_THREADS) {
+            const int yl = p >> 5, xl = p & 31;
+            if (X0 + xl <= X1) outp[(size_t)(ya + yl) * c.out_w + X0 + xl] = __fmul_rn((float)pcount[p], c.inv_samples);
+            pcount[p] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+} // namespace fg
+
+namespace {
+using namespace fg;
+
+struct TilePlan { TileCfg cfg; int spwc; bool ok; };
+
+inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+// Choose the strip geometry for a render; ok == false -> the tiled path does not apply.
+TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c) {
+    TilePlan pl{};
+    pl.ok = false;
+    if (c.rad.lognorm) return pl;                       // per-grain radii: direct kernel (for now)
+    if (p->n_samples > (1u << 20)) return pl;
+    const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
+    const double ox = (double)c.off_max_x - (double)c.off_min_x, oy = (double)c.off_max_y - (double)c.off_min_y;
+    const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0;
+    if (!(cwb < 2040.0)) return pl;
+    const int CWB = (int)cwb;
+    const int PS = CWB + 2;
+    const int R = std::max(1, std::min(15, 2048 / (CWB + 1)));
+    const int spwc = p->n_samples <= 64 ? 4 : (p->n_samples <= 128 ? 8 : 16);
+    const int band = c.row_end - c.row_begin;
+    const size_t smem_max = ctx->smem_optin;
+    // pass 0 insists that the grain ring holds the window at a plausible density (0.45 grains per
+    // cell; iid-uniform 8-bit input averages 1/pi); pass 1 takes anything that fits -- denser
+    // content overflows into the fallback list at run time.
+    for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
+        for (int gcap = 16384; gcap >= 2048 && !pl.ok; gcap >>= 1) {
+            for (int TH = 32; TH >= 1 && !pl.ok; TH >>= 1) {
+                if (TH > 1 && TH > 2 * band) continue;
+                const double rhb = ((TH - 1) * inv_zoom + oy + 2.0 * rm) / delta + 4.0;
+                if (!(rhb < 30000.0)) continue;
+                const int RH = (int)rhb;
+                TileCfg g{};
+                g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R; g.GCAP = gcap;
+                uint32_t off = 0;
+                g.off_col = off; off = align_up(off + (uint32_t)CWB * 16u, 16);
+                g.off_G = off; off = align_up(off + (uint32_t)gcap * 8u, 16);
+                g.off_P = off; off = align_up(off + (uint32_t)RH * PS * 2u, 16);
+                g.off_list = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
+                g.off_E = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
+                g.off_cnt = off; off = align_up(off + 132u * 4u, 16);
+                g.off_wtot = off; off = align_up(off + 20u * 4u, 16);
+                g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
+                g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
+                g.total = off;
+                if (off > smem_max) continue;
+                if (pass == 0 && (double)gcap < 0.45 * (double)RH * (double)CWB) continue;
+                pl.cfg = g;
+                pl.ok = true;
+            }
+        }
+    }
+    if (!pl.ok) return pl;
+    TileCfg& g = pl.cfg;
+    g.n_strips = (int)((p->out_w + 31) / 32);
+    // segment height: ~128 rows, shorter when the grid would not fill the machine
+    int seg = std::max(g.TH, 128 / g.TH * g.TH);
+    const int units_target = 3 * ctx->sm_count;
+    while (seg > 4 * g.TH && (long long)g.n_strips * ((band + seg - 1) / seg) < units_target) seg = std::max(4 * g.TH, seg / 2 / g.TH * g.TH);
+    g.SEG = seg;
+    g.n_segs = (band + seg - 1) / seg;
+    pl.spwc = spwc;
+    return pl;
+}
+
+int tile_setup(fg_ctx* ctx) {
+    cudaError_t e;
+    const int smem = (int)ctx->smem_optin;
+    if ((e = cudaFuncSetAttribute(k_pixelwise_strip<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_strip)");
+    return FG_OK;
+}
+
+// returns FG_OK (rendered), 1 (not applicable: caller uses the direct kernel) or an error
+int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
+                const float* d_offsets, float* d_out) {
+    TilePlan pl = tile_plan(ctx, p, c);
+    if (!pl.ok) return 1;
+    const TileCfg& g = pl.cfg;
+    const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
+    const size_t n_in = in_stride * n_planes;
+    const uint32_t units = (uint32_t)g.n_strips * g.n_segs * n_planes;
+    int rc;
+    if ((rc = ensure(ctx, ctx->thr, n_in * 16))) return rc;
+    if ((rc = ensure(ctx, ctx->tiles, (size_t)units * sizeof(TileRef) + 64))) return rc;
+    uint64_t* d_thr = (uint64_t*)ctx->thr.p;
+    double* d_e = (double*)((unsigned char*)ctx->thr.p + n_in * 8);
+    uint32_t* d_fbcount = (uint32_t*)ctx->tiles.p;
+    TileRef* d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
+    cudaStream_t s = ctx->stream;
+    FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+    const unsigned tb = (unsigned)std::min<size_t>((n_in + 255) / 256, (size_t)ctx->sm_count * 16);
+    k_thresholds<<<tb, 256, 0, s>>>(d_lambda, n_in, p->delta, d_thr, d_e);
+    FG_CUDA(ctx, cudaGetLastError());
+    const float2* off = (const float2*)d_offsets;
+    switch (pl.spwc) {
+    case 4: k_pixelwise_strip<4><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
+    case 8: k_pixelwise_strip<8><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
+    default: k_pixelwise_strip<16><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
+    }
+    FG_CUDA(ctx, cudaGetLastError());
+    const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);
+    const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units * chunks, (uint64_t)ctx->sm_count * 8);
+    k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
+                                                 chunks, c);
+    FG_CUDA(ctx, cudaGetLastError());
+    FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host, d_fbcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ctx->stats.launches += 3;
+    ctx->stats.tiles_total = units;
+    ctx->fb_pending = true;
+    return FG_OK;
+}
+
+} // namespace

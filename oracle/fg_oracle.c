@@ -790,6 +790,22 @@ uint32_t fgo_gen_cell(const fgo_params* p, const fgo_derived* d, int which_strea
     return q;
 }
 
+void fgo_gen_cells(const fgo_params* p, const fgo_derived* d, int which_stream, const int32_t* ij,
+                   const float* lambda_cell, size_t n, uint32_t cap, uint32_t* q_out, float* grains_out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < (int64_t)n; ++t) {
+        float cx[64], cy[64], r[64];
+        uint32_t c2 = cap < 64 ? cap : 64;
+        uint32_t q = fgo_gen_cell(p, d, which_stream, ij[2 * t], ij[2 * t + 1], lambda_cell[t], cx, cy, r, c2);
+        q_out[t] = q;
+        for (uint32_t g = 0; g < cap; ++g) {
+            float* o = grains_out + ((size_t)t * cap + g) * 3;
+            if (g < q && g < c2) { o[0] = cx[g]; o[1] = cy[g]; o[2] = r[g]; }
+            else { o[0] = o[1] = o[2] = 0.0f; }
+        }
+    }
+}
+
 /* ------------------------------------------------------------ src/color.rs ---- */
 static const float Y_COEFF_R = 0.2126f, Y_COEFF_G = 0.7152f, Y_COEFF_B = 0.0722f; /* color.rs:9-11 */
 static const float CB_DENOM = 1.8556f, CR_DENOM = 1.5748f;                        /* color.rs:12-13 */

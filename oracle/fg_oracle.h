@@ -139,6 +139,11 @@ uint32_t fgo_gen_cell(const fgo_params* p, const fgo_derived* d, int which_strea
                       int32_t j, float lambda_cell, float* cx, float* cy, float* rad,
                       uint32_t cap);
 
+/* batched fgo_gen_cell: ij n x [i,j]; q_out n; grains_out n x cap x [cx,cy,r] (zero-filled) */
+void fgo_gen_cells(const fgo_params* p, const fgo_derived* d, int which_stream, const int32_t* ij,
+                   const float* lambda_cell, size_t n, uint32_t cap, uint32_t* q_out,
+                   float* grains_out);
+
 /* ---- colour (color.rs) ---------------------------------------------------------- */
 void fgo_load_rgb_u8(const uint8_t* rgb, size_t npix, float* r, float* g, float* b);/* :158-179 */
 void fgo_load_luma_u8(const uint8_t* rgb, size_t npix, float* y, float* cb, float* cr);/* :181-213 */

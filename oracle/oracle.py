@@ -102,6 +102,7 @@ def lib() -> C.CDLL:
         "fgo_render_pixelwise": (C.c_int, [P(f32), P(Params), P(Derived), P(f32), P(f32), i64, i64, C.c_int, P(Counters)]),
         "fgo_render_grainwise": (C.c_int, [P(f32), P(Params), P(Derived), P(f32), P(f32), C.c_int, P(Counters)]),
         "fgo_gen_cell": (u32, [P(Params), P(Derived), C.c_int, i32, i32, f32, P(f32), P(f32), P(f32), u32]),
+        "fgo_gen_cells": (None, [P(Params), P(Derived), C.c_int, P(i32), P(f32), C.c_size_t, u32, P(u32), P(f32)]),
         "fgo_load_rgb_u8": (None, [P(C.c_uint8), C.c_size_t, P(f32), P(f32), P(f32)]),
         "fgo_load_luma_u8": (None, [P(C.c_uint8), C.c_size_t, P(f32), P(f32), P(f32)]),
         "fgo_store_rgb_u8": (None, [P(f32), P(f32), P(f32), C.c_size_t, P(C.c_uint8)]),
@@ -231,6 +232,18 @@ def gen_cell(p: Params, d: Derived, stream: int, i: int, j: int, lam: float, cap
     q = lib().fgo_gen_cell(C.byref(p), C.byref(d), stream, i, j, lam, _fp(cx), _fp(cy), _fp(r), cap)
     n = min(q, cap)
     return q, cx[:n], cy[:n], r[:n]
+
+
+def gen_cells(p: Params, d: Derived, stream: int, ij: np.ndarray, lam: np.ndarray, cap: int = 8):
+    """batched gen_cell -> (q[n] u32, grains[n,cap,3] f32)."""
+    ij = np.ascontiguousarray(ij, np.int32)
+    lam = np.ascontiguousarray(lam, np.float32)
+    n = ij.shape[0]
+    q = np.zeros(n, np.uint32)
+    g = np.zeros((n, cap, 3), np.float32)
+    lib().fgo_gen_cells(C.byref(p), C.byref(d), stream, ij.ctypes.data_as(C.POINTER(C.c_int32)), _fp(lam), n, cap,
+                        q.ctypes.data_as(C.POINTER(C.c_uint32)), _fp(g))
+    return q, g
 
 
 def render_rgb8(rgb: np.ndarray, p: Params, color_mode: int, nthreads: int = 0, counters: Counters | None = None):
