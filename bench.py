@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the film-grain hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (our engine)
+    python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU path, timed on host cores)
+
+Metric (BASELINE.json): Mpixel*samples/s = W_out*H_out*N / seconds / 1e6 (an RGB pixel counts once)
+on BASELINE.json configs[1]: pixel-wise RGB 3840x2160 synthetic noise, radius 0.1, 256 iterations.
+A "step" is one full render of the image (3 colour planes).
+
+  value : inputs (lambda planes, offsets) resident in HBM; device time (CUDA events on the engine's
+          stream) from the first kernel to the finished image resident on GPU 0 (bands gathered with
+          NCCL for N > 1); max over ranks.
+  e2e   : the same render through the reference-facing C-ABI call with HOST buffers
+          (fg_render_planes: f32 lambda planes in, f32 planes out; copies inside the timed region).
+  roofline : ALU-issue roofline (the path is integer/FP32-ALU bound, not HBM- or tensor-bound):
+          achieved = algorithmic lane-ops (SURVEY.md 8(d) op model with oracle-counted n_cell /
+          n_test) / strip-kernel time; peak = FFMA issue rate measured in this run.
+  cpu_baseline : the CPU oracle (a port of the reference's CPU path) timed on this box's host
+          cores on a bounded band of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (w, h, image, color planes, ParamsBuilder kwargs)   -- BASELINE.json configs
+    "c1": dict(w=512, h=512, image="gradient", planes=1, radius=0.1, n=64, zoom=1.0, algo="pixel",
+               desc="pixel-wise luma 512x512 gradient r=0.1 N=64"),
+    "c2": dict(w=3840, h=2160, image="noise", planes=3, radius=0.1, n=256, zoom=1.0, algo="pixel",
+               desc="pixel-wise RGB 3840x2160 noise r=0.1 N=256"),
+    "c3": dict(w=4096, h=4096, image="noise", planes=1, radius=0.5, n=128, zoom=1.0, algo="grain",
+               desc="grain-wise luma 4096x4096 noise r=0.5 N=128"),
+    "c4": dict(w=2048, h=2048, image="noise", planes=3, radius=0.05, n=64, zoom=4.0, algo="pixel",
+               desc="pixel-wise RGB 2048x2048 zoom 4 (8192x8192 out) r=0.05 N=64"),
+    "c5": dict(w=1024, h=1024, image="noise", planes=1, radius=0.12, n=1024, zoom=1.0, algo="pixel",
+               desc="pixel-wise luma 1024x1024 r=0.12 N=1024 (high-sample sweep point)"),
+}
+
+
+def synth_image(kind: str, w: int, h: int) -> np.ndarray:
+    """Deterministic 8-bit inputs; same generators as tests/helpers.py."""
+    if kind == "gradient":
+        row = np.rint(np.tile(np.linspace(0, 1, w), (h, 1)) * 255).astype(np.uint8)
+        return np.repeat(row[:, :, None], 3, axis=2)
+    return np.random.default_rng(20240611).integers(0, 256, (h, w, 3), dtype=np.uint8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows: list[list[str]] = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self) -> dict:
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_sample(wl: dict, img: np.ndarray, seconds: float, nthreads: int = 0):
+    """Time the CPU oracle (port of src/pixelwise.rs / src/grainwise.rs) on a bounded sample of the
+    workload.  Returns rate in plane-sample-evals/s plus the work counters of the sample."""
+    from oracle import oracle as O
+    algo = O.ALGO_PIXEL if wl["algo"] == "pixel" else O.ALGO_GRAIN
+    p = O.make_params(radius=wl["radius"], n_samples=wl["n"], zoom=wl["zoom"], algo=algo)
+    if wl["algo"] == "pixel":
+        d, off, off_in = O.derive_common(p, wl["w"], wl["h"])
+        plane = (img[:, :, 0].astype(np.float32) / np.float32(255.0)).astype(np.float32)
+        lam = O.lambda_plane(O.normalize_plane(plane), d.inv_e_pi_r2)
+        oh = d.output_height
+        y0 = oh // 2
+        c = O.Counters()
+        t = time.perf_counter()
+        O.render_pixelwise(lam, p, d, off_in, y0, y0 + 1, nthreads, c)  # calibration row
+        dt = max(time.perf_counter() - t, 1e-4)
+        threads = O.lib().fgo_max_threads() if nthreads <= 0 else nthreads
+        # one row ran on one thread: all threads do ~threads rows in the same time
+        rows = int(max(threads, min(oh - y0, threads * seconds / dt)))
+        c = O.Counters()
+        t = time.perf_counter()
+        O.render_pixelwise(lam, p, d, off_in, y0, y0 + rows, nthreads, c)
+        dt = time.perf_counter() - t
+        evals = c.sample_evals
+        return dict(rate=evals / dt, seconds=dt, threads=threads, rows=rows, evals=evals,
+                    n_cell=c.cell_visits / max(1, evals), n_test=c.grain_tests / max(1, evals),
+                    sample=f"{rows} output rows x {d.output_width} px x {wl['n']} samples of plane 0, {threads} threads")
+    # grain-wise: a centred square crop sized for the budget
+    threads = O.lib().fgo_max_threads() if nthreads <= 0 else nthreads
+    side = 256
+    while True:
+        crop = np.ascontiguousarray(img[:side, :side, 0])
+        d, off, off_in = O.derive_common(p, side, side)
+        plane = (crop.astype(np.float32) / np.float32(255.0)).astype(np.float32)
+        lam = O.lambda_plane(O.normalize_plane(plane), d.inv_e_pi_r2)
+        c = O.Counters()
+        t = time.perf_counter()
+        O.render_grainwise(lam, p, d, off, nthreads, c)
+        dt = time.perf_counter() - t
+        if dt > seconds / 4 or side * 2 > min(wl["w"], wl["h"]):
+            break
+        side *= 2
+    evals = d.output_width * d.output_height * wl["n"]
+    return dict(rate=evals / dt, seconds=dt, threads=threads, rows=side, evals=evals, n_cell=0.0, n_test=0.0,
+                sample=f"{side}x{side} crop x {wl['n']} samples, {threads} threads")
+
+
+def algorithmic_ops(wl: dict, d_block, off_in: np.ndarray, n_cell: float, n_test: float) -> dict:
+    """ops = S*(A_setup + n_cell*A_cell + n_test*A_test) + G*A_gen (lane-ops)."""
+    A_SETUP, A_CELL, A_TEST, A_GEN = 18, 3, 6, 200
+    S = float(wl["planes"]) * d_block.out_w * d_block.out_h * wl["n"]
+    inv_zoom = 1.0 / wl["zoom"]
+    span_x = (d_block.out_w * inv_zoom + float(off_in[:, 0].max() - off_in[:, 0].min()) + 2 * d_block.rm) / d_block.delta
+    span_y = (d_block.out_h * inv_zoom + float(off_in[:, 1].max() - off_in[:, 1].min()) + 2 * d_block.rm) / d_block.delta
+    G = float(wl["planes"]) * span_x * span_y
+    ops = S * (A_SETUP + n_cell * A_CELL + n_test * A_TEST) + G * A_GEN
+    return dict(ops=ops, S=S, G=G, ops_per_eval=ops / S)
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be
+    built in this image (no cargo/rustc), so this is the oracle port (kind 'port'), all host threads."""
+    if rank != 0:
+        return
+    img = synth_image(wl["image"], wl["w"], wl["h"])
+    per_step = max(2.0, min(12.0, 90.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        oracle_sample(wl, img, per_step / 4)
+    rates, last = [], None
+    for _ in range(args.steps):
+        last = oracle_sample(wl, img, per_step)
+        rates.append(last["rate"])
+    rate = float(np.mean(rates))
+    planes = wl["planes"]
+    value = rate / planes / 1e6
+    S_full = planes * (wl["w"] * wl["zoom"]) * (wl["h"] * wl["zoom"]) * wl["n"]
+    line = {
+        "impl": "reference", "metric": "Mpixel*samples/s", "value": value, "unit": "Mpixel*samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": S_full / rate * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample": last["sample"],
+                   "note": "rate measured on the bounded sample; ms_per_step extrapolated to the full workload"},
+        "cpu_baseline": {"value": value, "unit": "Mpixel*samples/s", "cores": last["threads"], "kind": "port",
+                         "sample": last["sample"]},
+        "e2e": {"value": value, "unit": "Mpixel*samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line, default=float), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import film_grain_b200 as fg
+    from film_grain_b200 import host as H
+    from film_grain_b200.dist import band_rows, gather_bands
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    # ---- host-side derivation exactly as the reference host does it (ParamsBuilder -> Derived) ----
+    img = synth_image(wl["image"], wl["w"], wl["h"])
+    params = H.ParamsBuilder(radius_mean=wl["radius"], n_samples=wl["n"], zoom=wl["zoom"],
+                             algo=H.Algo.Pixel if wl["algo"] == "pixel" else H.Algo.Grain,
+                             color_mode=H.ColorMode.Rgb if wl["planes"] == 3 else H.ColorMode.Luma).build()
+    d = H.derive_common(params, (wl["w"], wl["h"]))
+    planes = wl["planes"]
+    lam_host = [H.lambda_plane((img[:, :, c].astype(np.float32) / np.float32(255.0)).astype(np.float32), d.inv_e_pi_r2)
+                for c in range(planes)]
+    offsets = d.offsets_input if wl["algo"] == "pixel" else d.offsets
+    algo = fg.FG_ALGO_PIXEL if wl["algo"] == "pixel" else fg.FG_ALGO_GRAIN
+    out_w, out_h = d.output_width, d.output_height
+    rb, re = band_rows(out_h, rank, world)
+    blk = H._band(d.block, (rb, re) if world > 1 else None)
+
+    ctx = fg.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    d_lam = torch.from_numpy(np.stack(lam_host)).to(dev)
+    d_off = torch.from_numpy(np.ascontiguousarray(offsets)).to(dev)
+    d_out = torch.zeros((planes, out_h, out_w), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_device():
+        ctx.render_planes_device(blk, algo, planes, d_lam.data_ptr(), d_off.data_ptr(), d_out.data_ptr(), sync=False)
+        if world > 1:  # finished image resident on GPU 0: gather the row bands (NCCL over NVLink)
+            band = d_out[:, rb:re, :].permute(1, 0, 2).contiguous()
+            full = gather_bands(band, out_h, rank, world)
+            return full
+        return d_out
+
+    launches = 0
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        stream.synchronize()
+        st = ctx.stats()
+        launches_per_step = int(st.launches)
+        tiles_total, tiles_fb = int(st.tiles_total), int(st.tiles_fallback)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        strip_ms = []
+        for a, b in evs:
+            flush.zero_()  # L2 flush between timed iterations (outside the timed events)
+            a.record(stream)
+            step_device()
+            b.record(stream)
+            stream.synchronize()
+            strip_ms.append(float(ctx.stats().strip_ms))
+            launches += launches_per_step
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    tt = torch.tensor([total_ms, float(np.sum(strip_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, strip_total_ms = float(tt[0]), float(tt[1])
+    ms_per_step = total_ms / args.steps
+    value = out_w * out_h * wl["n"] / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: the reference-facing C-ABI call with HOST buffers (copies inside the timed region) ----
+    e2e = None
+    host_outs = [np.zeros((out_h, out_w), np.float32) for _ in range(planes)]
+    if world == 1:
+        for _ in range(2):
+            ctx.render_planes(blk, algo, lam_host, offsets, host_outs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ctx.render_planes(blk, algo, lam_host, offsets, host_outs)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        s = ctx.stats()
+        e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
+               "h2d_bytes_per_step": int(s.h2d_bytes), "d2h_bytes_per_step": int(s.d2h_bytes),
+               "ms_per_step": e2e_ms, "h2d_ms": float(s.h2d_ms), "kernel_ms": float(s.kernel_ms), "d2h_ms": float(s.d2h_ms),
+               "call": "fg_render_planes (host f32 lambda planes in, f32 planes out)"}
+        # the fused u8 entry point: 8-bit RGB over PCIe instead of f32 planes
+        if planes == 3 and wl["algo"] == "pixel":
+            out8 = np.zeros((out_h, out_w, 3), np.uint8)
+            for _ in range(2):
+                ctx.render_rgb8(blk, algo, fg.FG_COLOR_RGB, img, offsets, out8)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ctx.render_rgb8(blk, algo, fg.FG_COLOR_RGB, img, offsets, out8)
+            f_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            s8 = ctx.stats()
+            e2e["fused_rgb8"] = {"value": out_w * out_h * wl["n"] / (f_ms * 1e-3) / 1e6, "ms_per_step": f_ms,
+                                 "h2d_bytes_per_step": int(s8.h2d_bytes), "d2h_bytes_per_step": int(s8.d2h_bytes),
+                                 "call": "fg_render_rgb8 (host u8 RGB in/out, colour fused on device)"}
+    else:
+        pin_in = torch.from_numpy(np.stack(lam_host)).pin_memory()
+        pin_out = torch.empty((out_h, planes, out_w), dtype=torch.float32).pin_memory() if rank == 0 else None
+        with torch.cuda.stream(stream):
+            def step_e2e():
+                d_lam.copy_(pin_in, non_blocking=True)
+                full = step_device()
+                if rank == 0:
+                    pin_out.copy_(full, non_blocking=True)
+            step_e2e()
+            stream.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                step_e2e()
+                stream.synchronize()
+            dist.barrier()
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t2[0])
+        e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
+               "h2d_bytes_per_step": int(pin_in.numel() * 4), "d2h_bytes_per_step": int(planes * out_w * out_h * 4),
+               "ms_per_step": e2e_ms,
+               "call": "per rank: pinned H2D of the lambda planes + band render + NCCL band gather; rank 0: D2H of the image"}
+
+    if rank == 0:
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0
+        issue = ctx.measure_issue_peak()
+        cpu, roof = None, None
+        n_cell, n_test = 6.6, 1.6
+        if world == 1 and not args.no_cpu:
+            sm = oracle_sample(wl, img, args.cpu_seconds)
+            n_cell, n_test = (sm["n_cell"], sm["n_test"]) if wl["algo"] == "pixel" else (n_cell, n_test)
+            cpu = {"value": sm["rate"] / planes / 1e6, "unit": "Mpixel*samples/s", "cores": sm["threads"], "kind": "port",
+                   "sample": sm["sample"], "seconds": sm["seconds"]}
+        if wl["algo"] == "pixel":
+            ao = algorithmic_ops(wl, d.block, d.offsets_input, n_cell, n_test)
+            kernel_ms = (strip_total_ms / args.steps) if strip_total_ms > 0 else ms_per_step
+            achieved = ao["ops"] / (kernel_ms * 1e-3) / 1e12
+            traffic = None
+            prof = os.path.join(ROOT, "profiles", "strip_dram_bytes.json")
+            if os.path.exists(prof):
+                try:
+                    traffic = json.load(open(prof)).get(args.workload)
+                except Exception:
+                    traffic = None
+            io_bytes = planes * (wl["w"] * wl["h"] * 16 + out_w * out_h * 4)  # thr+e planes in, f32 plane out
+            roof = {"bound": "alu", "achieved": achieved, "peak": issue["ffma"] / 1e3, "unit": "Tlane-op/s",
+                    "frac": achieved / (issue["ffma"] / 1e3), "traffic": traffic,
+                    "kernel": "k_pixelwise_strip", "kernel_ms": kernel_ms, "share_of_step": kernel_ms / ms_per_step,
+                    "ops_model": {"A_setup": 18, "A_cell": 3, "A_test": 6, "A_gen": 200, "n_cell": n_cell, "n_test": n_test,
+                                  "sample_evals": ao["S"], "cells": ao["G"], "ops_per_sample_eval": ao["ops_per_eval"],
+                                  "counted_by": "oracle sample" if cpu else "default"},
+                    "peak_source": "FFMA issue rate measured in this run (fg_measure_issue_peak); IMAD is half rate",
+                    "issue_peaks_glaneops": issue,
+                    "hbm": {"achieved_gbs": io_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                            "frac": io_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_file) else "fallback"}}
+        line = {
+            "metric": "Mpixel*samples/s", "value": value, "unit": "Mpixel*samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "seed": 5489, "sigma_px": 0.8, "algo": wl["algo"],
+                       "parallelism": f"row-bands x{world}" if world > 1 else "single GPU",
+                       "l2": "flushed between timed iterations (256 MiB memset outside the events)",
+                       "tiles": tiles_total, "tiles_fallback": tiles_fb},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line, default=float), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,7 +35,25 @@ class FgStats(C.Structure):
     """struct fg_stats (include/fg.h)."""
     _fields_ = [("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("launches", C.c_uint32), ("tiles_total", C.c_uint32), ("tiles_fallback", C.c_uint32),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("strip_ms", C.c_float), ("reserved", C.c_uint32)]
+
+
+class FghParams(C.Structure):
+    """struct fgh_params (include/fg_host.h) = ParamsBuilder (src/params.rs:70-91)."""
+    _fields_ = [("radius_dist", C.c_int32), ("radius_mean", C.c_float), ("radius_stddev", C.c_float),
+                ("zoom", C.c_float), ("sigma_px", C.c_float), ("n_samples", C.c_uint32), ("algo", C.c_int32),
+                ("max_radius_kind", C.c_int32), ("max_radius_value", C.c_float), ("has_cell_delta", C.c_int32),
+                ("cell_delta", C.c_float), ("color_mode", C.c_int32), ("has_size", C.c_int32),
+                ("size_w", C.c_uint32), ("has_size_h", C.c_int32), ("size_h", C.c_uint32), ("seed", C.c_uint64)]
+
+
+class FghDerived(C.Structure):
+    """struct fgh_derived (include/fg_host.h) = Derived (src/model.rs:167-179) + resolved algorithm."""
+    _fields_ = [("input_width", C.c_uint64), ("input_height", C.c_uint64), ("output_width", C.c_uint64),
+                ("output_height", C.c_uint64), ("inv_e_pi_r2", C.c_float), ("rm", C.c_float), ("delta", C.c_float),
+                ("radius_stddev", C.c_float), ("has_log", C.c_int32), ("algorithm", C.c_int32),
+                ("log_mu", C.c_double), ("log_sigma", C.c_double), ("block", FgParams)]
 
 
 # every symbol include/fg.h declares: name -> (restype, argtypes)
@@ -61,6 +79,16 @@ ABI = {
     "fg_dump_cells": (C.c_int, [_VP, _P(FgParams), C.c_int, _VP, _VP, C.c_size_t, C.c_uint32, _VP, _VP]),
     "fg_measure_issue_peak": (C.c_int, [_VP, _P(C.c_double)]),
 }
+# include/fg_host.h (host-side mirror of the reference's library API)
+HOST_ABI = {
+    "fgh_last_error": (C.c_char_p, []),
+    "fgh_derive": (C.c_int, [_P(FghParams), C.c_uint64, C.c_uint64, _P(FghDerived), _VP, _VP]),
+    "fgh_lambda_from_plane": (C.c_int, [_VP, C.c_uint64, C.c_uint64, C.c_float, _VP]),
+    "fgh_render_with_input_image": (C.c_int, [_P(FghParams), _VP, C.c_uint64, C.c_uint64, C.c_int, C.c_int,
+                                              _P(C.c_int), _VP, C.c_uint64, _P(FghDerived)]),
+    "fgh_context": (_VP, [C.c_int]),
+    "fgh_invalidate_context": (None, []),
+}
 
 _lib = None
 
@@ -78,7 +106,7 @@ def load() -> C.CDLL:
         raise EngineMissing(f"{SO_PATH} not built: run `python film_grain_b200/build.py` "
                             "(or __graft_entry__.build()); there is no CPU fallback")
     lib = C.CDLL(SO_PATH)
-    for name, (res, args) in ABI.items():
+    for name, (res, args) in list(ABI.items()) + list(HOST_ABI.items()):
         try:
             fn = getattr(lib, name)
         except AttributeError as e:

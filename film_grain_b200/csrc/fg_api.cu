@@ -325,7 +325,12 @@ void fg_set_cancel_flag(fg_ctx* ctx, const volatile int* flag) { if (ctx) ctx->c
 void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
     if (!ctx || !out) return;
     *out = ctx->stats;
-    if (ctx->fb_pending) out->tiles_fallback = ctx->fb_count_host; // meaningful once the stream is synchronised
+    if (ctx->fb_pending) { // meaningful once the stream is synchronised
+        out->tiles_fallback = ctx->fb_count_host;
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) out->strip_ms = ms;
+        else cudaGetLastError();
+    }
 }
 uint64_t fg_context_stream(const fg_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
 

@@ -506,12 +506,14 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
     k_thresholds<<<tb, 256, 0, s>>>(d_lambda, n_in, p->delta, d_thr, d_e);
     FG_CUDA(ctx, cudaGetLastError());
     const float2* off = (const float2*)d_offsets;
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
     switch (pl.spwc) {
     case 4: k_pixelwise_strip<4><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
     case 8: k_pixelwise_strip<8><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
     default: k_pixelwise_strip<16><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
     }
     FG_CUDA(ctx, cudaGetLastError());
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
     const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);
     const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units * chunks, (uint64_t)ctx->sm_count * 8);
     k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,

@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing: contiguous output row bands per rank and the gather of the
+finished bands.  One process per GPU (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+
+The path shards into fully independent units: every output pixel depends only on (seed, offsets,
+lambda in a bounded neighbourhood), and grains are pure functions of (seed, i, j, lambda(cell))
+(src/rng.rs:26-34, src/pixelwise.rs:68-82).  Each rank therefore renders its band with the margin
+cells regenerated locally -- there is no halo exchange and no data-path collective; the only
+communication is the gather of the final image.
+"""
+from __future__ import annotations
+
+
+def band_rows(out_h: int, rank: int, world: int) -> tuple[int, int]:
+    """Rows [begin, end) of `rank`: contiguous, disjoint, covering [0, out_h), sizes differ by <= 1."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, rem = divmod(out_h, world)
+    begin = rank * base + min(rank, rem)
+    end = begin + base + (1 if rank < rem else 0)
+    return begin, end
+
+
+def max_band_rows(out_h: int, world: int) -> int:
+    return (out_h + world - 1) // world
+
+
+def gather_bands(band, out_h: int, rank: int, world: int, dst: int = 0, group=None):
+    """Gather per-rank bands [..., rows_r, W(, C)] (row axis = -2 for planes [P,rows,W]; pass tensors whose
+    dim 0 is the row axis) to `dst`.  Bands are padded to the common maximum so one collective moves
+    everything; returns the assembled [out_h, ...] tensor on dst, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return band
+    mx = max_band_rows(out_h, world)
+    rows = band.shape[0]
+    if rows < mx:
+        pad = torch.zeros((mx - rows,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+        band = torch.cat([band, pad], dim=0)
+    band = band.contiguous()
+    if rank == dst:
+        parts = [torch.empty_like(band) for _ in range(world)]
+        dist.gather(band, parts, dst=dst, group=group)
+        pieces = []
+        for r in range(world):
+            b, e = band_rows(out_h, r, world)
+            pieces.append(parts[r][: e - b])
+        return torch.cat(pieces, dim=0)
+    dist.gather(band, None, dst=dst, group=group)
+    return None

@@ -92,6 +92,8 @@ typedef struct fg_stats {
     uint32_t tiles_total;     /* pixel-wise tiled path: tiles rendered */
     uint32_t tiles_fallback;  /*   of which re-rendered by the direct kernel (capacity / lambda>=12) */
     uint64_t h2d_bytes, d2h_bytes;
+    float strip_ms;           /* pixel-wise tiled path: device time of the strip kernel alone */
+    uint32_t reserved;
 } fg_stats;
 
 int fg_abi_version(void);
