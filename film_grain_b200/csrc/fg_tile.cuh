@@ -71,6 +71,8 @@ struct TileCfg {
 #define FG_TILE_THREADS 512
 #define FG_TILE_WARPS 16
 #define FG_TILE_ITERS 4 // phase-A cells per thread per group: R*(CW+1) <= 2048
+#define FG_TILE_GPAD 4  // grain ring entries mirrored past the end (unrolled reads never wrap)
+#define FG_TILE_USLOTS 3 // unrolled, predicated grain tests per cell-row range
 
 __device__ __forceinline__ void push_fallback(TileRef* list, uint32_t* count, uint32_t cap, int x0, int y0, int w,
                                               int h, int plane) {
@@ -85,6 +87,28 @@ __device__ __forceinline__ void push_fallback(TileRef* list, uint32_t* count, ui
 // floor((v -/+ rm) / delta) exactly as src/pixelwise.rs:55-58
 __device__ __forceinline__ int cell_lo(float v, float rm, float delta) { return floor_i32(__fdiv_rn(__fsub_rn(v, rm), delta)); }
 __device__ __forceinline__ int cell_hi(float v, float rm, float delta) { return floor_i32(__fdiv_rn(__fadd_rn(v, rm), delta)); }
+
+// explicit shared-window loads (32-bit addresses): keeps the hot loop free of generic-pointer
+// window arithmetic.  volatile: never cached across the CTA barriers that separate generation
+// from evaluation.
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
+// packed byte offsets of P[row][i0 - i_lo] and P[row][i1 - i_lo + 1] for sample abscissa xg (0 = no cells).
+// Out of line on purpose: two IEEE divisions per call, 16 call sites in the unrolled sample loop.
+__device__ __noinline__ uint32_t col_range_packed(float xg, float rm, float delta, int i_lo) {
+    const int i0 = cell_lo(xg, rm, delta), i1 = cell_hi(xg, rm, delta);
+    if (i0 > i1) return 0u;
+    return (uint32_t)(2 * (i0 - i_lo)) | ((uint32_t)(2 * (i1 - i_lo + 1)) << 16);
+}
 
 template <int SPWC>
 __global__ void __launch_bounds__(FG_TILE_THREADS, 1)
@@ -140,8 +164,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
         int i = i_lo + il;
         ci.h = mix3_col(c.seed_cell, i);
         ci.sx = __fmul_rn(__int2float_rn(i), delta);
-        long long ix = floor_i64(ci.sx);
-        ci.ixc = (int)(ix < 0 ? 0 : (ix > c.in_w - 1 ? c.in_w - 1 : ix));
+        ci.ixc = min(max(floor_i32(ci.sx), 0), c.in_w - 1);
         colT[il] = ci;
     }
     for (int p = tid; p < cfg.TH * 32; p += FG_TILE_THREADS) pcount[p] = 0;
@@ -172,14 +195,13 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
             if (k < c.n && xvalid) {
                 float2 o = __ldg(offsets_input + k);
                 xg = __fsub_rn(bx, o.x);
-                int i0 = cell_lo(xg, rm, delta), i1 = cell_hi(xg, rm, delta);
-                if (i0 <= i1) ip = (uint32_t)(i0 - i_lo) | ((uint32_t)(i1 - i_lo + 1) << 16);
+                ip = col_range_packed(xg, rm, delta, i_lo);
             }
             xg_r[s] = xg;
             ip_r[s] = ip;
         }
     };
-    if (n_chunks == 1) load_xk(0);
+    bool xk_loaded = false;
     __syncthreads();
 
     // ---- ring state (uniform across the CTA) ----
@@ -187,6 +209,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     int j_gen = 0, rr_gen = 0;    // next cell row to generate and its ring row
     int j_lo_prev = 0, rr_lo = 0; // oldest live cell row and its ring row
     bool first = true;
+    int r_cur = cfg.R;            // rows per generation group (adapts to the non-empty fraction)
 
     for (int ya = Y0; ya < Y1; ya += cfg.TH) {
         const int yb = min(ya + cfg.TH, Y1) - 1; // inclusive
@@ -212,31 +235,37 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
         }
         uint32_t used = (j_lo < j_gen) ? ((head - (uint32_t)P[rr_lo * PS]) & 0xFFFFu) : 0u;
 
-        // =================== generation: cell rows j_gen .. j_hi in groups of R ===================
+        // =================== generation: cell rows j_gen .. j_hi in groups of <= R rows ===================
         while (j_gen <= j_hi) {
-            const int nr = min(cfg.R, j_hi - j_gen + 1);
-            // ---- phase A: first-draw filter on every cell of the group ----
+            const int nr = min(r_cur, j_hi - j_gen + 1);
+            // ---- phase A: first-draw filter on every cell of the group (4 independent hash chains
+            //      per thread are issued back to back before the ballots) ----
             uint32_t masks[FG_TILE_ITERS];
+            bool ne[FG_TILE_ITERS];
+            bool general = false;
 #pragma unroll
             for (int it = 0; it < FG_TILE_ITERS; ++it) {
-                bool nonempty = false;
+                ne[it] = false;
                 const int rc = rci[it];
                 if (rc >= 0 && (rc >> 16) < nr && (rc & 0xFFFF) < CW) {
                     const int il = rc & 0xFFFF, j = j_gen + (rc >> 16);
                     const ColInfo ci = colT[il];
-                    const float sy = __fmul_rn(__int2float_rn(j), delta);
-                    long long iy = floor_i64(sy);
-                    iy = iy < 0 ? 0 : (iy > c.in_h - 1 ? c.in_h - 1 : iy);
+                    int iy = floor_i32(__fmul_rn(__int2float_rn(j), delta));
+                    iy = min(max(iy, 0), c.in_h - 1);
                     const uint64_t th64 = __ldg(thr + (size_t)iy * c.in_w + ci.ixc);
                     const uint64_t h = mix3_row(ci.h, j);
                     uint64_t s0, s3;
                     if (c.seeding == 0) { s0 = pcg_word_pair<0>(h); s3 = pcg_word_pair<3>(h); }
                     else { Xoshiro t; seed_splitmix(t, h); s0 = t.s0; s3 = t.s3; }
                     const uint64_t m1 = (rotl64(s0 + s3, 23) + s0) >> 11;
-                    if (th64 == FG_THR_GENERAL) wtot[16] = 1;
-                    else nonempty = m1 > th64;
+                    general |= (th64 == FG_THR_GENERAL);
+                    ne[it] = (th64 != FG_THR_GENERAL) && (m1 > th64);
                 }
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, nonempty);
+            }
+            if (general) wtot[16] = 1;
+#pragma unroll
+            for (int it = 0; it < FG_TILE_ITERS; ++it) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne[it]);
                 masks[it] = m;
                 if (lane == 0) cntA[it * 16 + warp] = __popc(m);
             }
@@ -280,8 +309,8 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                     const ColInfo ci = colT[il];
                     sx = ci.sx;
                     sy = __fmul_rn(__int2float_rn(j), delta);
-                    long long iy = floor_i64(sy);
-                    iy = iy < 0 ? 0 : (iy > c.in_h - 1 ? c.in_h - 1 : iy);
+                    int iy = floor_i32(sy);
+                    iy = min(max(iy, 0), c.in_h - 1);
                     const double e = __ldg(ev + (size_t)iy * c.in_w + ci.ixc);
                     seed_small_rng(rng, mix3_row(ci.h, j), c.seeding);
                     double p = standard_f64(rng); // first draw (known > e)
@@ -313,7 +342,9 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                     for (uint32_t g = 0; g < q; ++g) {
                         float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
                         float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
-                        G[(pos + g) & GM] = make_float2(cx, cy);
+                        const uint32_t gi = (pos + g) & GM;
+                        G[gi] = make_float2(cx, cy);
+                        if (gi < FG_TILE_GPAD) G[cfg.GCAP + gi] = make_float2(cx, cy); // mirror: reads never wrap
                     }
                 }
                 head += total;
@@ -336,13 +367,16 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
             j_gen += nr;
             rr_gen += nr;
             if (rr_gen >= RH) rr_gen -= RH;
+            // next group: as many rows as keep the dense pass within one sweep of the CTA
+            r_cur = (int)min((uint32_t)cfg.R, max(1u, (uint32_t)(FG_TILE_THREADS - 32) * (uint32_t)nr / max(M, 1u)));
             __syncthreads();
         }
 
         // =================== evaluation of pixel rows ya..yb ===================
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
-            if (n_chunks > 1) load_xk(chunk);
-            // per-(row, sample) data of this warp: sample point y and its cell-row range
+            if (n_chunks > 1 || !xk_loaded) { load_xk(chunk); xk_loaded = true; }
+            // per-(row, sample) data of this warp: sample point y, byte offset of its first cell row in P
+            // (bits 0-23) and the number of cell rows (bits 24-31)
             float2* wp = wpair + warp * (cfg.TH * SPWC);
             for (int qd = lane; qd < th * SPWC; qd += 32) {
                 const int s = qd / th, yl = qd - s * th;
@@ -356,13 +390,15 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                     if (j0 <= j1) {
                         int rr = rr_lo + (j0 - j_lo);
                         if (rr >= RH) rr -= RH;
-                        jp = (uint32_t)rr | ((uint32_t)(j1 - j0 + 1) << 16);
+                        jp = (uint32_t)(rr * PS * 2) | ((uint32_t)(j1 - j0 + 1) << 24);
                     }
                 }
                 wp[s * th + yl] = make_float2(yg, __uint_as_float(jp));
             }
             __syncwarp();
             if (xvalid && radius_ok) {
+                const uint32_t Ps = (uint32_t)__cvta_generic_to_shared(P), Gs = (uint32_t)__cvta_generic_to_shared(G);
+                const uint32_t PS2 = (uint32_t)PS * 2u, RHPS2 = (uint32_t)RH * PS2;
                 for (int yl = 0; yl < th; ++yl) {
                     uint32_t cnt = 0;
 #pragma unroll
@@ -370,26 +406,37 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                         const float2 pd = wp[s * th + yl];
                         const uint32_t jp = __float_as_uint(pd.y);
                         const uint32_t ip = ip_r[s];
-                        const int a = ip & 0xFFFF, b = ip >> 16;
-                        int nrow = (a < b) ? (int)(jp >> 16) : 0;
-                        int rr = jp & 0xFFFF;
+                        const uint32_t a2 = ip & 0xFFFFu, b2 = ip >> 16;
+                        const uint32_t nrow = (a2 != b2) ? (jp >> 24) : 0u;
+                        uint32_t off = Ps + (jp & 0xFFFFFFu);
                         const float xg = xg_r[s], yg = pd.x;
-                        bool covered = false;
-                        while (nrow > 0 && !covered) {
-                            const uint16_t* prow = P + rr * PS;
-                            const uint32_t s16 = prow[a], e16 = prow[b];
-                            uint32_t n = (e16 - s16) & 0xFFFFu;
-                            uint32_t idx = s16;
-                            while (n > 0) {
-                                const float2 gr = G[idx & GM];
+                        uint32_t covered = 0;
+                        // per cell row (trip count is warp-uniform): FG_TILE_USLOTS straight-line predicated
+                        // grain tests, then a remainder loop that exits on the first hit
+#pragma unroll 1
+                        for (uint32_t r = 0; r < nrow; ++r) {
+                            const uint32_t s16 = lds_u16(off + a2), e16 = lds_u16(off + b2);
+                            const uint32_t n = (e16 - s16) & 0xFFFFu;
+                            const uint32_t ga = Gs + (s16 & GM) * 8u;
+#pragma unroll
+                            for (int u = 0; u < FG_TILE_USLOTS; ++u) {
+                                const float2 gr = lds_f32x2(ga + 8u * u); // beyond n: stale but in-bounds (mirror pad), masked below
                                 const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
-                                if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= r2) { covered = true; break; }
-                                ++idx; --n;
+                                const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                covered |= ((uint32_t)u < n && d2 <= r2) ? 1u : 0u;
                             }
-                            ++rr; if (rr >= RH) rr = 0;
-                            --nrow;
+                            if (n > FG_TILE_USLOTS && !covered) { // > 3 grains in the cell range and none of the first 3 covers
+                                uint32_t u = FG_TILE_USLOTS;
+                                do {
+                                    const float2 gr = lds_f32x2(Gs + ((s16 + u) & GM) * 8u);
+                                    const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
+                                    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= r2) { covered = 1u; break; }
+                                } while (++u < n);
+                            }
+                            off += PS2;
+                            if (off >= Ps + RHPS2) off = Ps;
                         }
-                        cnt += covered ? 1u : 0u;
+                        cnt += covered;
                     }
                     if (cnt) atomicAdd(&pcount[yl * 32 + lane], cnt);
                 }
@@ -425,6 +472,7 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c)
     const double ox = (double)c.off_max_x - (double)c.off_min_x, oy = (double)c.off_max_y - (double)c.off_min_y;
     const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0;
     if (!(cwb < 2040.0)) return pl;
+    if (!(2.0 * rm / delta + 3.0 < 250.0)) return pl;   // cell rows per sample are packed in 8 bits
     const int CWB = (int)cwb;
     const int PS = CWB + 2;
     const int R = std::max(1, std::min(15, 2048 / (CWB + 1)));
@@ -445,7 +493,7 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c)
                 g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R; g.GCAP = gcap;
                 uint32_t off = 0;
                 g.off_col = off; off = align_up(off + (uint32_t)CWB * 16u, 16);
-                g.off_G = off; off = align_up(off + (uint32_t)gcap * 8u, 16);
+                g.off_G = off; off = align_up(off + (uint32_t)(gcap + FG_TILE_GPAD) * 8u, 16);
                 g.off_P = off; off = align_up(off + (uint32_t)RH * PS * 2u, 16);
                 g.off_list = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
                 g.off_E = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
