@@ -376,8 +376,9 @@ def main():
                 except Exception:
                     traffic = None
             io_bytes = planes * (wl["w"] * wl["h"] * 16 + out_w * out_h * 4)  # thr+e planes in, f32 plane out
-            roof = {"bound": "alu", "achieved": achieved, "peak": issue["ffma"] / 1e3, "unit": "Tlane-op/s",
-                    "frac": achieved / (issue["ffma"] / 1e3), "traffic": traffic,
+            peak = issue["ffma"] / 1e3 * world  # aggregate over the GPUs that shared the launch's work
+            roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
+                    "frac": achieved / peak, "traffic": traffic,
                     "kernel": "k_pixelwise_strip", "kernel_ms": kernel_ms, "share_of_step": kernel_ms / ms_per_step,
                     "ops_model": {"A_setup": 18, "A_cell": 3, "A_test": 6, "A_gen": 200, "n_cell": n_cell, "n_test": n_test,
                                   "sample_evals": ao["S"], "cells": ao["G"], "ops_per_sample_eval": ao["ops_per_eval"],
@@ -398,9 +399,17 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }
         print(json.dumps(line, default=float), flush=True)
-    ctx.close()
+    # teardown: torch's device and pinned-host allocators record events on every stream a block was
+    # used on -- including the engine's stream -- when blocks are released at interpreter exit, i.e.
+    # after the context may already have destroyed that stream.  Synchronise, tear the process group
+    # down, and leave without running destructors.
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -270,29 +270,37 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                 if (lane == 0) cntA[it * 16 + warp] = __popc(m);
             }
             __syncthreads();
-            if (warp == 0) { // exclusive scan of the 64 (it, warp) counts
-                uint32_t a = cntA[2 * lane], b = cntA[2 * lane + 1];
-                uint32_t s = a + b, incl = s;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                uint32_t excl = incl - s;
-                cntA[64 + 2 * lane] = excl;
-                cntA[64 + 2 * lane + 1] = excl + a;
-                if (lane == 31) cntA[128] = incl;
-            }
-            __syncthreads();
             if (wtot[16]) { // a cell of this group needs the general path: hand the rest of the segment over
                 if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
                 return;
             }
-            const uint32_t M = cntA[128];
+            // exclusive scan of the 64 (it, warp) counts, redundantly in every warp (no extra barrier):
+            // lane l holds entries 2l, 2l+1; the offsets this thread needs come back by shuffle
+            uint32_t offs[FG_TILE_ITERS];
+            uint32_t M;
+            {
+                const uint32_t a = cntA[2 * lane], b = cntA[2 * lane + 1];
+                const uint32_t s = a + b;
+                uint32_t incl = s;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const uint32_t excl = incl - s;
+                M = __shfl_sync(0xFFFFFFFFu, incl, 31);
+#pragma unroll
+                for (int it = 0; it < FG_TILE_ITERS; ++it) {
+                    const int e = it * 16 + warp;
+                    const uint32_t ex = __shfl_sync(0xFFFFFFFFu, excl, e >> 1);
+                    const uint32_t av = __shfl_sync(0xFFFFFFFFu, a, e >> 1);
+                    offs[it] = ex + ((e & 1) ? av : 0u);
+                }
+            }
 #pragma unroll
             for (int it = 0; it < FG_TILE_ITERS; ++it) {
                 if ((masks[it] >> lane) & 1u) {
-                    uint32_t pos = cntA[64 + it * 16 + warp] + __popc(masks[it] & lt_mask);
+                    const uint32_t pos = offs[it] + __popc(masks[it] & lt_mask);
                     list[pos] = (uint16_t)(((rci[it] >> 16) << 12) | (rci[it] & 0xFFF));
                 }
             }
@@ -351,26 +359,27 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                 used += total;
                 __syncthreads(); // wtot reuse + E/G visible
             }
-            if (tid == 0) E[M] = (uint16_t)head;
-            __syncthreads();
             // ---- P fill: ring position of the first grain at or after each cell ----
 #pragma unroll
             for (int it = 0; it < FG_TILE_ITERS; ++it) {
                 const int rc = rci[it];
                 if (rc >= 0 && (rc >> 16) < nr) {
-                    uint32_t rank = cntA[64 + it * 16 + warp] + __popc(masks[it] & lt_mask);
+                    const uint32_t rank = offs[it] + __popc(masks[it] & lt_mask);
                     int rr = rr_gen + (rc >> 16);
                     if (rr >= RH) rr -= RH;
-                    P[rr * PS + (rc & 0xFFFF)] = E[rank];
+                    P[rr * PS + (rc & 0xFFFF)] = (rank == M) ? (uint16_t)head : E[rank];
                 }
             }
             j_gen += nr;
             rr_gen += nr;
             if (rr_gen >= RH) rr_gen -= RH;
             // next group: as many rows as keep the dense pass within one sweep of the CTA
-            r_cur = (int)min((uint32_t)cfg.R, max(1u, (uint32_t)(FG_TILE_THREADS - 32) * (uint32_t)nr / max(M, 1u)));
-            __syncthreads();
+            if (M > (uint32_t)(FG_TILE_THREADS - 16)) r_cur = max(1, nr - 1);
+            else if (M * (uint32_t)(nr + 1) <= (uint32_t)(FG_TILE_THREADS - 32) * (uint32_t)nr) r_cur = min(cfg.R, nr + 1);
+            else r_cur = nr;
+            // no barrier here: the next group only touches cntA/list/E behind its own barriers
         }
+        __syncthreads(); // P and G complete before the evaluation reads them
 
         // =================== evaluation of pixel rows ya..yb ===================
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
@@ -410,9 +419,12 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                         const uint32_t nrow = (a2 != b2) ? (jp >> 24) : 0u;
                         uint32_t off = Ps + (jp & 0xFFFFFFu);
                         const float xg = xg_r[s], yg = pd.x;
-                        uint32_t covered = 0;
-                        // per cell row (trip count is warp-uniform): FG_TILE_USLOTS straight-line predicated
-                        // grain tests, then a remainder loop that exits on the first hit
+                        // per cell row (trip count is warp-uniform): FG_TILE_USLOTS straight-line grain tests
+                        // folded into a running minimum of the squared distance (slots past the range's
+                        // end are neutralised by an infinite abscissa), then a remainder loop that exits on
+                        // the first hit.  min() over candidates, one compare per sample: same boolean as
+                        // the reference's per-grain `dx*dx + dy*dy <= r*r`.
+                        float dmin = __int_as_float(0x7f800000);
 #pragma unroll 1
                         for (uint32_t r = 0; r < nrow; ++r) {
                             const uint32_t s16 = lds_u16(off + a2), e16 = lds_u16(off + b2);
@@ -420,22 +432,24 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                             const uint32_t ga = Gs + (s16 & GM) * 8u;
 #pragma unroll
                             for (int u = 0; u < FG_TILE_USLOTS; ++u) {
-                                const float2 gr = lds_f32x2(ga + 8u * u); // beyond n: stale but in-bounds (mirror pad), masked below
-                                const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
-                                const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                                covered |= ((uint32_t)u < n && d2 <= r2) ? 1u : 0u;
+                                const float2 gr = lds_f32x2(ga + 8u * u); // beyond n: stale but in-bounds (mirror pad)
+                                const float gx = ((uint32_t)u < n) ? gr.x : __int_as_float(0x7f800000);
+                                const float dx = __fsub_rn(xg, gx), dy = __fsub_rn(yg, gr.y);
+                                dmin = fminf(dmin, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
                             }
-                            if (n > FG_TILE_USLOTS && !covered) { // > 3 grains in the cell range and none of the first 3 covers
+                            if (n > FG_TILE_USLOTS && !(dmin <= r2)) { // > 3 grains in the range, none of the first 3 covers
                                 uint32_t u = FG_TILE_USLOTS;
                                 do {
                                     const float2 gr = lds_f32x2(Gs + ((s16 + u) & GM) * 8u);
                                     const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
-                                    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= r2) { covered = 1u; break; }
+                                    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    if (d2 <= r2) { dmin = d2; break; }
                                 } while (++u < n);
                             }
                             off += PS2;
                             if (off >= Ps + RHPS2) off = Ps;
                         }
+                        const uint32_t covered = (dmin <= r2) ? 1u : 0u;
                         cnt += covered;
                     }
                     if (cnt) atomicAdd(&pcount[yl * 32 + lane], cnt);
