@@ -410,47 +410,66 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                 const uint32_t PS2 = (uint32_t)PS * 2u, RHPS2 = (uint32_t)RH * PS2;
                 for (int yl = 0; yl < th; ++yl) {
                     uint32_t cnt = 0;
+                    // two samples (A, B) advance through their cell rows together: their shared-memory
+                    // loads are issued stage by stage (prefixes of A and B, then grains of A and B, then
+                    // the arithmetic), which doubles the independent work in flight per warp.
 #pragma unroll
-                    for (int s = 0; s < SPWC; ++s) {
-                        const float2 pd = wp[s * th + yl];
-                        const uint32_t jp = __float_as_uint(pd.y);
-                        const uint32_t ip = ip_r[s];
-                        const uint32_t a2 = ip & 0xFFFFu, b2 = ip >> 16;
-                        const uint32_t nrow = (a2 != b2) ? (jp >> 24) : 0u;
-                        uint32_t off = Ps + (jp & 0xFFFFFFu);
-                        const float xg = xg_r[s], yg = pd.x;
-                        // per cell row (trip count is warp-uniform): FG_TILE_USLOTS straight-line grain tests
-                        // folded into a running minimum of the squared distance (slots past the range's
-                        // end are neutralised by an infinite abscissa), then a remainder loop that exits on
-                        // the first hit.  min() over candidates, one compare per sample: same boolean as
-                        // the reference's per-grain `dx*dx + dy*dy <= r*r`.
-                        float dmin = __int_as_float(0x7f800000);
+                    for (int s = 0; s < SPWC; s += 2) {
+                        const float2 pdA = wp[s * th + yl], pdB = wp[(s + 1) * th + yl];
+                        const uint32_t jpA = __float_as_uint(pdA.y), jpB = __float_as_uint(pdB.y);
+                        const uint32_t a2A = ip_r[s] & 0xFFFFu, b2A = ip_r[s] >> 16;
+                        const uint32_t a2B = ip_r[s + 1] & 0xFFFFu, b2B = ip_r[s + 1] >> 16;
+                        const uint32_t nrowA = (a2A != b2A) ? (jpA >> 24) : 0u, nrowB = (a2B != b2B) ? (jpB >> 24) : 0u;
+                        uint32_t offA = Ps + (jpA & 0xFFFFFFu), offB = Ps + (jpB & 0xFFFFFFu);
+                        const float xgA = xg_r[s], ygA = pdA.x, xgB = xg_r[s + 1], ygB = pdB.x;
+                        float dminA = __int_as_float(0x7f800000), dminB = __int_as_float(0x7f800000);
+                        const uint32_t nmax = max(nrowA, nrowB);
 #pragma unroll 1
-                        for (uint32_t r = 0; r < nrow; ++r) {
-                            const uint32_t s16 = lds_u16(off + a2), e16 = lds_u16(off + b2);
-                            const uint32_t n = (e16 - s16) & 0xFFFFu;
-                            const uint32_t ga = Gs + (s16 & GM) * 8u;
+                        for (uint32_t r = 0; r < nmax; ++r) {
+                            // a sample that has run out of cell rows reads an empty range (b := a)
+                            const uint32_t bA = (r < nrowA) ? b2A : a2A, bB = (r < nrowB) ? b2B : a2B;
+                            const uint32_t sA = lds_u16(offA + a2A), eA = lds_u16(offA + bA);
+                            const uint32_t sB = lds_u16(offB + a2B), eB = lds_u16(offB + bB);
+                            const uint32_t nA = (eA - sA) & 0xFFFFu, nB = (eB - sB) & 0xFFFFu;
+                            const uint32_t gaA = Gs + (sA & GM) * 8u, gaB = Gs + (sB & GM) * 8u;
+                            float2 gA[FG_TILE_USLOTS], gB[FG_TILE_USLOTS];
+#pragma unroll
+                            for (int u = 0; u < FG_TILE_USLOTS; ++u) gA[u] = lds_f32x2(gaA + 8u * u); // past n: stale, in-bounds
+#pragma unroll
+                            for (int u = 0; u < FG_TILE_USLOTS; ++u) gB[u] = lds_f32x2(gaB + 8u * u);
 #pragma unroll
                             for (int u = 0; u < FG_TILE_USLOTS; ++u) {
-                                const float2 gr = lds_f32x2(ga + 8u * u); // beyond n: stale but in-bounds (mirror pad)
-                                const float gx = ((uint32_t)u < n) ? gr.x : __int_as_float(0x7f800000);
-                                const float dx = __fsub_rn(xg, gx), dy = __fsub_rn(yg, gr.y);
-                                dmin = fminf(dmin, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                                const float gxA = ((uint32_t)u < nA) ? gA[u].x : __int_as_float(0x7f800000);
+                                const float gxB = ((uint32_t)u < nB) ? gB[u].x : __int_as_float(0x7f800000);
+                                const float dxA = __fsub_rn(xgA, gxA), dyA = __fsub_rn(ygA, gA[u].y);
+                                const float dxB = __fsub_rn(xgB, gxB), dyB = __fsub_rn(ygB, gB[u].y);
+                                dminA = fminf(dminA, __fadd_rn(__fmul_rn(dxA, dxA), __fmul_rn(dyA, dyA)));
+                                dminB = fminf(dminB, __fadd_rn(__fmul_rn(dxB, dxB), __fmul_rn(dyB, dyB)));
                             }
-                            if (n > FG_TILE_USLOTS && !(dmin <= r2)) { // > 3 grains in the range, none of the first 3 covers
+                            if (nA > FG_TILE_USLOTS && !(dminA <= r2)) { // remainder: exits on the first hit
                                 uint32_t u = FG_TILE_USLOTS;
                                 do {
-                                    const float2 gr = lds_f32x2(Gs + ((s16 + u) & GM) * 8u);
-                                    const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
+                                    const float2 gr = lds_f32x2(Gs + ((sA + u) & GM) * 8u);
+                                    const float dx = __fsub_rn(xgA, gr.x), dy = __fsub_rn(ygA, gr.y);
                                     const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-                                    if (d2 <= r2) { dmin = d2; break; }
-                                } while (++u < n);
+                                    if (d2 <= r2) { dminA = d2; break; }
+                                } while (++u < nA);
                             }
-                            off += PS2;
-                            if (off >= Ps + RHPS2) off = Ps;
+                            if (nB > FG_TILE_USLOTS && !(dminB <= r2)) {
+                                uint32_t u = FG_TILE_USLOTS;
+                                do {
+                                    const float2 gr = lds_f32x2(Gs + ((sB + u) & GM) * 8u);
+                                    const float dx = __fsub_rn(xgB, gr.x), dy = __fsub_rn(ygB, gr.y);
+                                    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    if (d2 <= r2) { dminB = d2; break; }
+                                } while (++u < nB);
+                            }
+                            offA += PS2;
+                            if (offA >= Ps + RHPS2) offA = Ps;
+                            offB += PS2;
+                            if (offB >= Ps + RHPS2) offB = Ps;
                         }
-                        const uint32_t covered = (dmin <= r2) ? 1u : 0u;
-                        cnt += covered;
+                        cnt += ((dminA <= r2) ? 1u : 0u) + ((dminB <= r2) ? 1u : 0u);
                     }
                     if (cnt) atomicAdd(&pcount[yl * 32 + lane], cnt);
                 }
@@ -477,7 +496,7 @@ struct TilePlan { TileCfg cfg; int spwc; bool ok; };
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // Choose the strip geometry for a render; ok == false -> the tiled path does not apply.
-TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c) {
+TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes) {
     TilePlan pl{};
     pl.ok = false;
     if (c.rad.lognorm) return pl;                       // per-grain radii: direct kernel (for now)
@@ -526,10 +545,24 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c)
     if (!pl.ok) return pl;
     TileCfg& g = pl.cfg;
     g.n_strips = (int)((p->out_w + 31) / 32);
-    // segment height: ~128 rows, shorter when the grid would not fill the machine
-    int seg = std::max(g.TH, 128 / g.TH * g.TH);
-    const int units_target = 3 * ctx->sm_count;
-    while (seg > 4 * g.TH && (long long)g.n_strips * ((band + seg - 1) / seg) < units_target) seg = std::max(4 * g.TH, seg / 2 / g.TH * g.TH);
+    // segment height: maximise (wave efficiency over the SMs) x (1 - start-up share).  A segment
+    // regenerates the cell rows of its first window (RH rows = RH*delta*zoom pixel rows of work).
+    const double startup_rows = (double)g.RH * delta * (double)p->zoom;
+    const long long per_seg_units = (long long)g.n_strips * n_planes;
+    int best_n = 1;
+    double best_eff = -1.0;
+    const int max_n = std::max(1, band / std::max(1, 4 * g.TH));
+    for (int n = 1; n <= max_n; ++n) {
+        int seg = (band + n - 1) / n;
+        seg = (seg + g.TH - 1) / g.TH * g.TH;
+        const int n_eff = (band + seg - 1) / seg;
+        const double units = (double)per_seg_units * n_eff;
+        const double waves = units / ctx->sm_count;
+        const double eff = waves / std::ceil(waves) * ((double)seg / ((double)seg + startup_rows));
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_n = n; }
+    }
+    int seg = (band + best_n - 1) / best_n;
+    seg = (seg + g.TH - 1) / g.TH * g.TH;
     g.SEG = seg;
     g.n_segs = (band + seg - 1) / seg;
     pl.spwc = spwc;
@@ -549,7 +582,7 @@ int tile_setup(fg_ctx* ctx) {
 // returns FG_OK (rendered), 1 (not applicable: caller uses the direct kernel) or an error
 int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
                 const float* d_offsets, float* d_out) {
-    TilePlan pl = tile_plan(ctx, p, c);
+    TilePlan pl = tile_plan(ctx, p, c, n_planes);
     if (!pl.ok) return 1;
     const TileCfg& g = pl.cfg;
     const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
