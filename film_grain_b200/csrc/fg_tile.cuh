@@ -68,9 +68,18 @@ struct TileCfg {
     uint32_t off_col, off_P, off_G, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, total;
 };
 
-#define FG_TILE_THREADS 512
+#ifndef FG_TILE_WARPS
 #define FG_TILE_WARPS 16
-#define FG_TILE_ITERS 4 // phase-A cells per thread per group: R*(CW+1) <= 2048
+#endif
+#define FG_TILE_THREADS (FG_TILE_WARPS * 32)
+#define FG_TILE_ITERS 4 // phase-A cells per thread per group: R*(CW+1) <= FG_TILE_CELLS
+#define FG_TILE_CELLS (FG_TILE_THREADS * FG_TILE_ITERS)
+#define FG_TILE_NE (FG_TILE_ITERS * FG_TILE_WARPS) // (iteration, warp) compaction counters
+#if FG_TILE_WARPS == 16
+#define FG_TILE_SPW_MAX 16 // samples per warp per chunk (even): N <= 256 in one chunk
+#else
+#define FG_TILE_SPW_MAX 14 // 20 warps x 14 = 280 >= 256
+#endif
 #define FG_TILE_GPAD 4  // grain ring entries mirrored past the end (unrolled reads never wrap)
 #define FG_TILE_USLOTS 3 // unrolled, predicated grain tests per cell-row range
 
@@ -123,7 +132,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     uint16_t* list = (uint16_t*)(smem + cfg.off_list);
     uint16_t* E = (uint16_t*)(smem + cfg.off_E);
     uint32_t* cntA = (uint32_t*)(smem + cfg.off_cnt);  // [64] counts, [64..128] exclusive offsets, [128] total
-    uint32_t* wtot = (uint32_t*)(smem + cfg.off_wtot); // [16] warp totals, [16] flag
+    uint32_t* wtot = (uint32_t*)(smem + cfg.off_wtot); // [NW] warp totals, [NW] general-path flag
     uint32_t* pcount = (uint32_t*)(smem + cfg.off_pcount);
     float2* wpair = (float2*)(smem + cfg.off_wpair);
 
@@ -168,7 +177,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
         colT[il] = ci;
     }
     for (int p = tid; p < cfg.TH * 32; p += FG_TILE_THREADS) pcount[p] = 0;
-    if (tid == 0) wtot[16] = 0;
+    if (tid == 0) wtot[FG_TILE_WARPS] = 0;
 
     // phase-A cell assignment of this thread: cell c = tid + 512*it -> (r, il), il == CW is the row sentinel
     int rci[FG_TILE_ITERS];
@@ -185,11 +194,11 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     const float bx = __fmul_rn(__fadd_rn((float)x, 0.5f), c.inv_zoom);
     float xg_r[SPWC];
     uint32_t ip_r[SPWC];
-    const int n_chunks = (int)((c.n + 16 * SPWC - 1) / (16 * SPWC));
+    const int n_chunks = (int)((c.n + FG_TILE_WARPS * SPWC - 1) / (FG_TILE_WARPS * SPWC));
     auto load_xk = [&](int chunk) {
 #pragma unroll
         for (int s = 0; s < SPWC; ++s) {
-            uint32_t k = (uint32_t)chunk * (16 * SPWC) + s * 16 + warp;
+            uint32_t k = (uint32_t)chunk * (FG_TILE_WARPS * SPWC) + s * FG_TILE_WARPS + warp;
             float xg = 0.0f;
             uint32_t ip = 0;
             if (k < c.n && xvalid) {
@@ -262,25 +271,28 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                     ne[it] = (th64 != FG_THR_GENERAL) && (m1 > th64);
                 }
             }
-            if (general) wtot[16] = 1;
+            if (general) wtot[FG_TILE_WARPS] = 1;
 #pragma unroll
             for (int it = 0; it < FG_TILE_ITERS; ++it) {
                 const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne[it]);
                 masks[it] = m;
-                if (lane == 0) cntA[it * 16 + warp] = __popc(m);
+                if (lane == 0) cntA[it * FG_TILE_WARPS + warp] = __popc(m);
             }
             __syncthreads();
-            if (wtot[16]) { // a cell of this group needs the general path: hand the rest of the segment over
+            if (wtot[FG_TILE_WARPS]) { // a cell of this group needs the general path: hand the rest of the segment over
                 if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
                 return;
             }
-            // exclusive scan of the 64 (it, warp) counts, redundantly in every warp (no extra barrier):
-            // lane l holds entries 2l, 2l+1; the offsets this thread needs come back by shuffle
+            // exclusive scan of the FG_TILE_NE (it, warp) counts, redundantly in every warp (no extra
+            // barrier): lane l holds entries 3l..3l+2; the offsets this thread needs come back by shuffle
             uint32_t offs[FG_TILE_ITERS];
             uint32_t M;
             {
-                const uint32_t a = cntA[2 * lane], b = cntA[2 * lane + 1];
-                const uint32_t s = a + b;
+                static_assert(FG_TILE_NE <= 96, "three counters per lane");
+                const uint32_t a = (3 * lane + 0 < FG_TILE_NE) ? cntA[3 * lane + 0] : 0u;
+                const uint32_t b = (3 * lane + 1 < FG_TILE_NE) ? cntA[3 * lane + 1] : 0u;
+                const uint32_t d3 = (3 * lane + 2 < FG_TILE_NE) ? cntA[3 * lane + 2] : 0u;
+                const uint32_t s = a + b + d3;
                 uint32_t incl = s;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -291,10 +303,12 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                 M = __shfl_sync(0xFFFFFFFFu, incl, 31);
 #pragma unroll
                 for (int it = 0; it < FG_TILE_ITERS; ++it) {
-                    const int e = it * 16 + warp;
-                    const uint32_t ex = __shfl_sync(0xFFFFFFFFu, excl, e >> 1);
-                    const uint32_t av = __shfl_sync(0xFFFFFFFFu, a, e >> 1);
-                    offs[it] = ex + ((e & 1) ? av : 0u);
+                    const int e = it * FG_TILE_WARPS + warp;
+                    const int src = e / 3, sub = e - 3 * src;
+                    const uint32_t ex = __shfl_sync(0xFFFFFFFFu, excl, src);
+                    const uint32_t av = __shfl_sync(0xFFFFFFFFu, a, src);
+                    const uint32_t bv = __shfl_sync(0xFFFFFFFFu, b, src);
+                    offs[it] = ex + (sub > 0 ? av : 0u) + (sub > 1 ? bv : 0u);
                 }
             }
 #pragma unroll
@@ -389,7 +403,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
             float2* wp = wpair + warp * (cfg.TH * SPWC);
             for (int qd = lane; qd < th * SPWC; qd += 32) {
                 const int s = qd / th, yl = qd - s * th;
-                const uint32_t k = (uint32_t)chunk * (16 * SPWC) + s * 16 + warp;
+                const uint32_t k = (uint32_t)chunk * (FG_TILE_WARPS * SPWC) + s * FG_TILE_WARPS + warp;
                 float yg = 0.0f;
                 uint32_t jp = 0;
                 if (k < c.n) {
@@ -508,8 +522,8 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     if (!(2.0 * rm / delta + 3.0 < 250.0)) return pl;   // cell rows per sample are packed in 8 bits
     const int CWB = (int)cwb;
     const int PS = CWB + 2;
-    const int R = std::max(1, std::min(15, 2048 / (CWB + 1)));
-    const int spwc = p->n_samples <= 64 ? 4 : (p->n_samples <= 128 ? 8 : 16);
+    const int R = std::max(1, std::min(15, FG_TILE_CELLS / (CWB + 1)));
+    const int spwc = p->n_samples <= 4u * FG_TILE_WARPS ? 4 : (p->n_samples <= 8u * FG_TILE_WARPS ? 8 : FG_TILE_SPW_MAX);
     const int band = c.row_end - c.row_begin;
     const size_t smem_max = ctx->smem_optin;
     // pass 0 insists that the grain ring holds the window at a plausible density (0.45 grains per
@@ -530,8 +544,8 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
                 g.off_P = off; off = align_up(off + (uint32_t)RH * PS * 2u, 16);
                 g.off_list = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
                 g.off_E = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
-                g.off_cnt = off; off = align_up(off + 132u * 4u, 16);
-                g.off_wtot = off; off = align_up(off + 20u * 4u, 16);
+                g.off_cnt = off; off = align_up(off + (uint32_t)(FG_TILE_NE + 8) * 4u, 16);
+                g.off_wtot = off; off = align_up(off + (uint32_t)(FG_TILE_WARPS + 4) * 4u, 16);
                 g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
                 g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
                 g.total = off;
@@ -552,15 +566,17 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     int best_n = 1;
     double best_eff = -1.0;
     const int max_n = std::max(1, band / std::max(1, 4 * g.TH));
-    for (int n = 1; n <= max_n; ++n) {
+    auto seg_eff = [&](int n) {
         int seg = (band + n - 1) / n;
         seg = (seg + g.TH - 1) / g.TH * g.TH;
         const int n_eff = (band + seg - 1) / seg;
-        const double units = (double)per_seg_units * n_eff;
-        const double waves = units / ctx->sm_count;
-        const double eff = waves / std::ceil(waves) * ((double)seg / ((double)seg + startup_rows));
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_n = n; }
-    }
+        const double waves = (double)per_seg_units * n_eff / ctx->sm_count;
+        return waves / std::ceil(waves) * ((double)seg / ((double)seg + startup_rows));
+    };
+    for (int n = 1; n <= max_n; ++n) best_eff = std::max(best_eff, seg_eff(n));
+    // among near-optimal splits prefer the finest one: more, shorter CTAs balance content-dependent cost
+    for (int n = 1; n <= max_n; ++n)
+        if (seg_eff(n) >= best_eff - 0.01) best_n = n;
     int seg = (band + best_n - 1) / best_n;
     seg = (seg + g.TH - 1) / g.TH * g.TH;
     g.SEG = seg;
@@ -574,7 +590,7 @@ int tile_setup(fg_ctx* ctx) {
     const int smem = (int)ctx->smem_optin;
     if ((e = cudaFuncSetAttribute(k_pixelwise_strip<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pixelwise_strip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<FG_TILE_SPW_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_strip)");
     return FG_OK;
 }
@@ -605,7 +621,7 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
     switch (pl.spwc) {
     case 4: k_pixelwise_strip<4><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
     case 8: k_pixelwise_strip<8><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
-    default: k_pixelwise_strip<16><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
+    default: k_pixelwise_strip<FG_TILE_SPW_MAX><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
     }
     FG_CUDA(ctx, cudaGetLastError());
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
