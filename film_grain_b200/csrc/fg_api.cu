@@ -173,9 +173,8 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
             if ((rc = ensure(ctx, ctx->grains, total * sizeof(GrainRec)))) return rc;
             k_gw_fill<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (const uint64_t*)ctx->scan_out.p, (GrainRec*)ctx->grains.p, c);
             FG_CUDA(ctx, cudaGetLastError());
-            const uint64_t work = total * (uint64_t)p->n_samples;
-            uint64_t want_blocks = (work + 255) / 256;
-            const uint64_t max_blocks = (uint64_t)ctx->sm_count * 32;
+            uint64_t want_blocks = (total + 255) / 256;
+            const uint64_t max_blocks = (uint64_t)ctx->sm_count * 64;
             unsigned sblocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
             k_gw_splat<<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
                                                          (uint32_t*)ctx->bits.p, lanes32, c);

@@ -216,33 +216,34 @@ __device__ __forceinline__ bool gw_bounds(float center, float radius, int limit,
     return true;
 }
 
-// One thread per (grain, sample k): rasterise the zoomed disk at centre+offset[k] and OR bit
-// k into the per-pixel coverage mask (src/grainwise.rs:66-101).
+// One thread per grain, looping over the N sample offsets (warp-uniform loads of offsets[k]):
+// rasterise the zoomed disk at centre+offset[k] and OR bit k into the per-pixel coverage mask
+// (src/grainwise.rs:66-101).  Lanes of a warp hold consecutive grains of the same input pixels, so
+// their atomics land on neighbouring mask words.
 __global__ void __launch_bounds__(256) k_gw_splat(const GrainRec* __restrict__ grains, const uint64_t* __restrict__ n_grains_ptr,
                                                    const float2* __restrict__ offsets, uint32_t* __restrict__ bits,
                                                    uint32_t lanes32, RenderConsts c) {
-    const uint64_t total = *n_grains_ptr * (uint64_t)c.n;
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t g = t / c.n;
-        uint32_t k = (uint32_t)(t - g * c.n);
-        GrainRec rec = grains[g];
+    const uint64_t total = *n_grains_ptr;
+    const int last_x = c.out_w - 1, lo_y = c.row_begin, hi_y = c.row_end - 1;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+        const GrainRec rec = grains[g];
         if (!(rec.radius_out > 0.0f)) continue;
-        float2 o = __ldg(offsets + k);
-        float tx = __fadd_rn(rec.cxz, o.x), ty = __fadd_rn(rec.cyz, o.y);
-        int x_min, x_max, y_min, y_max;
-        if (!gw_bounds(tx, rec.radius_out, c.out_w, 0, c.out_w - 1, x_min, x_max)) continue;
-        if (!gw_bounds(ty, rec.radius_out, c.out_h, c.row_begin, c.row_end - 1, y_min, y_max)) continue;
-        const uint32_t bit = 1u << (k & 31u);
-        const uint32_t lane = k >> 5;
-        for (int oy = y_min; oy <= y_max; ++oy) {
-            float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
-            float dy_sq = __fmul_rn(dy, dy);
-            if (dy_sq > rec.radius_sq) continue;
-            for (int ox = x_min; ox <= x_max; ++ox) {
-                float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
-                if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= rec.radius_sq) {
-                    size_t idx = (size_t)(oy - c.row_begin) * c.out_w + ox;
-                    atomicOr(bits + idx * lanes32 + lane, bit);
+        for (uint32_t k = 0; k < c.n; ++k) {
+            const float2 o = __ldg(offsets + k);
+            const float tx = __fadd_rn(rec.cxz, o.x), ty = __fadd_rn(rec.cyz, o.y);
+            int x_min, x_max, y_min, y_max;
+            if (!gw_bounds(tx, rec.radius_out, c.out_w, 0, last_x, x_min, x_max)) continue;
+            if (!gw_bounds(ty, rec.radius_out, c.out_h, lo_y, hi_y, y_min, y_max)) continue;
+            const uint32_t bit = 1u << (k & 31u);
+            const uint32_t lane = k >> 5;
+            for (int oy = y_min; oy <= y_max; ++oy) {
+                const float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
+                const float dy_sq = __fmul_rn(dy, dy);
+                if (dy_sq > rec.radius_sq) continue;
+                uint32_t* row = bits + ((size_t)(oy - c.row_begin) * c.out_w) * lanes32 + lane;
+                for (int ox = x_min; ox <= x_max; ++ox) {
+                    const float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
+                    if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= rec.radius_sq) atomicOr(row + (size_t)ox * lanes32, bit);
                 }
             }
         }

@@ -75,7 +75,9 @@ struct TileCfg {
 #define FG_TILE_ITERS 4 // phase-A cells per thread per group: R*(CW+1) <= FG_TILE_CELLS
 #define FG_TILE_CELLS (FG_TILE_THREADS * FG_TILE_ITERS)
 #define FG_TILE_NE (FG_TILE_ITERS * FG_TILE_WARPS) // (iteration, warp) compaction counters
-#if FG_TILE_WARPS == 16
+#if FG_TILE_WARPS == 32
+#define FG_TILE_SPW_MAX 8  // 32 warps x 8 = 256
+#elif FG_TILE_WARPS == 16
 #define FG_TILE_SPW_MAX 16 // samples per warp per chunk (even): N <= 256 in one chunk
 #else
 #define FG_TILE_SPW_MAX 14 // 20 warps x 14 = 280 >= 256
@@ -284,15 +286,19 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                 return;
             }
             // exclusive scan of the FG_TILE_NE (it, warp) counts, redundantly in every warp (no extra
-            // barrier): lane l holds entries 3l..3l+2; the offsets this thread needs come back by shuffle
+            // barrier): lane l holds entries K*l .. K*l+K-1; the offsets this thread needs come back by shuffle
             uint32_t offs[FG_TILE_ITERS];
             uint32_t M;
             {
-                static_assert(FG_TILE_NE <= 96, "three counters per lane");
-                const uint32_t a = (3 * lane + 0 < FG_TILE_NE) ? cntA[3 * lane + 0] : 0u;
-                const uint32_t b = (3 * lane + 1 < FG_TILE_NE) ? cntA[3 * lane + 1] : 0u;
-                const uint32_t d3 = (3 * lane + 2 < FG_TILE_NE) ? cntA[3 * lane + 2] : 0u;
-                const uint32_t s = a + b + d3;
+                constexpr int K = (FG_TILE_NE + 31) / 32;
+                static_assert(K <= 4, "at most four counters per lane");
+                uint32_t cv[K];
+                uint32_t s = 0;
+#pragma unroll
+                for (int q = 0; q < K; ++q) {
+                    cv[q] = (K * lane + q < FG_TILE_NE) ? cntA[K * lane + q] : 0u;
+                    s += cv[q];
+                }
                 uint32_t incl = s;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -304,11 +310,14 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
 #pragma unroll
                 for (int it = 0; it < FG_TILE_ITERS; ++it) {
                     const int e = it * FG_TILE_WARPS + warp;
-                    const int src = e / 3, sub = e - 3 * src;
-                    const uint32_t ex = __shfl_sync(0xFFFFFFFFu, excl, src);
-                    const uint32_t av = __shfl_sync(0xFFFFFFFFu, a, src);
-                    const uint32_t bv = __shfl_sync(0xFFFFFFFFu, b, src);
-                    offs[it] = ex + (sub > 0 ? av : 0u) + (sub > 1 ? bv : 0u);
+                    const int src = e / K, sub = e - K * src;
+                    uint32_t o = __shfl_sync(0xFFFFFFFFu, excl, src);
+#pragma unroll
+                    for (int q = 0; q < K - 1; ++q) {
+                        const uint32_t v = __shfl_sync(0xFFFFFFFFu, cv[q], src);
+                        if (q < sub) o += v;
+                    }
+                    offs[it] = o;
                 }
             }
 #pragma unroll
