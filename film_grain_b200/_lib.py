@@ -88,6 +88,7 @@ HOST_ABI = {
                                               _P(C.c_int), _VP, C.c_uint64, _P(FghDerived)]),
     "fgh_context": (_VP, [C.c_int]),
     "fgh_invalidate_context": (None, []),
+    "fgh_logf_restated": (None, [_VP, C.c_uint64, _VP]),
 }
 
 _lib = None

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfg_b200.so")
 SOURCES = ["fg_api.cu", os.path.join("..", "host", "film_grain.cpp")]
 DEPS = ["fg_api.cu", "fg_ctx.cuh", "fg_kernels.cuh", "fg_rng.cuh", "fg_tile.cuh", "fg_color.cuh",
-        "fg_zig_tables.h", os.path.join("..", "..", "include", "fg.h"), os.path.join("..", "..", "include", "fg_host.h"),
+        "fg_zig_tables.h", "fg_logf.h", os.path.join("..", "..", "include", "fg.h"), os.path.join("..", "..", "include", "fg_host.h"),
         os.path.join("..", "host", "film_grain.cpp"), os.path.join("..", "host", "film_grain.hpp")]
 
 

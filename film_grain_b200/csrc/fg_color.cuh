@@ -5,13 +5,14 @@
 //              src/model.rs:228-265), so lambda is bit-identical to what the Rust host computes;
 //              3 planes rendered in one batched launch; store = to_u8 (src/color.rs:98-112, 237-239).
 //   Luma mode: Y/Cb/Cr split (src/color.rs:181-213) with un-fused f32 arithmetic on the device;
-//              lambda(Y) needs logf per pixel: computed as (float)log((double)x), the correctly
-//              rounded value except within ~1e-9 of a rounding boundary -- host libm logf (glibc:
-//              <= 0.82 ulp) may differ from it in the last bit for some inputs, see DESIGN.md;
+//              lambda(Y) needs logf per pixel: fg_logf.h restates the libm algorithm the Rust host
+//              calls (glibc / musl logf; checked against libm over every positive normal float),
+//              so lambda is bit-identical here too;
 //              chroma nearest-resize (src/model.rs:77-98) + Y'CbCr -> RGB (src/color.rs:68-97).
 #pragma once
 #include "fg_ctx.cuh"
 #include "fg_kernels.cuh"
+#include "fg_logf.h"
 
 namespace {
 
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) k_load_luma(const uint8_t* __restrict__ r
         float hi = __fsub_rn(1.0f, EPS);
         float clamped = y < 0.0f ? 0.0f : (y > hi ? hi : y); // normalize_plane (max <= 1+eps branch) + lambda_plane clamp
         float safe = fmaxf(__fsub_rn(1.0f, clamped), EPS);
-        float ln = __double2float_rn(log((double)safe));
+        float ln = logf_libm(safe); // the host libm's logf, restated (fg_logf.h): bit-identical lambda
         float activity = __fmul_rn(-inv_e_pi_r2, ln);
         lambda[t] = fminf(activity, 1.0e6f);
     }

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "../csrc/fg_logf.h"
 #include "../csrc/fg_zig_tables.h"
 
 namespace film_grain {
@@ -636,5 +637,9 @@ fg_ctx* fgh_context(int device) {
 }
 
 void fgh_invalidate_context(void) { cuda::invalidate_context(); }
+
+void fgh_logf_restated(const float* x, uint64_t n, float* out) {
+    for (uint64_t k = 0; k < n; ++k) out[k] = fg::logf_libm(x[k]);
+}
 
 } // extern "C"

@@ -66,6 +66,9 @@ int fgh_render_with_input_image(const fgh_params* p, const uint8_t* rgb, uint64_
                                 uint64_t out_capacity, fgh_derived* info);
 fg_ctx* fgh_context(int device);       /* process-global cached context; NULL on failure */
 void fgh_invalidate_context(void);
+/* The libm logf restatement the fused luma path runs on the device (csrc/fg_logf.h), host build:
+ * lets the CPU tests compare it with the platform's logf. */
+void fgh_logf_restated(const float* x, uint64_t n, float* out);
 
 #ifdef __cplusplus
 }

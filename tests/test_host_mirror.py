@@ -115,3 +115,25 @@ def test_empty_input_is_an_error():
     p = H.ParamsBuilder().build()
     with pytest.raises(H.RenderError):
         H.derive_common(p, (0, 10))
+
+
+def test_restated_logf_matches_the_platform_libm():
+    """csrc/fg_logf.h (the logf the fused luma path runs on the device) vs this host's libm logf:
+    the Rust host's f32::ln is that libm call (src/model.rs:261).  tools/check_logf.c is the
+    exhaustive version (all positive normal floats, 0 differences on glibc 2.39)."""
+    import ctypes as C
+    from film_grain_b200 import _lib
+    L = _lib.load()
+    libm = C.CDLL("libm.so.6")
+    libm.logf.restype = C.c_float
+    libm.logf.argtypes = [C.c_float]
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.random(20000, dtype=np.float32), np.float32(1) - rng.random(5000, dtype=np.float32) * np.float32(1e-4),
+                        np.float32(1e-6) * (1 + rng.random(2000, dtype=np.float32)),
+                        (np.arange(1, 256, dtype=np.float32) / np.float32(255)),
+                        np.array([1e-6, 1.0, 0.5, 2.0, 1e-30, 3e38, 1.0000001, 0.99999994], np.float32)]).astype(np.float32)
+    x = x[x > 0]
+    out = np.empty_like(x)
+    L.fgh_logf_restated(C.c_void_p(x.ctypes.data), x.size, C.c_void_p(out.ctypes.data))
+    ref = np.array([libm.logf(float(v)) for v in x], np.float32)
+    assert np.array_equal(ref.view(np.uint32), out.view(np.uint32))
