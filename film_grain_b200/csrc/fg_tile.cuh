@@ -540,7 +540,9 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     // content overflows into the fallback list at run time.
     for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
         for (int gcap = 16384; gcap >= 2048 && !pl.ok; gcap >>= 1) {
-            for (int TH = 32; TH >= 1 && !pl.ok; TH >>= 1) {
+            static const int th_candidates[] = {32, 24, 16, 12, 8, 6, 4, 3, 2, 1};
+            for (int TH : th_candidates) {
+                if (pl.ok) break;
                 if (TH > 1 && TH > 2 * band) continue;
                 const double rhb = ((TH - 1) * inv_zoom + oy + 2.0 * rm) / delta + 4.0;
                 if (!(rhb < 30000.0)) continue;
