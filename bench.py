@@ -328,11 +328,15 @@ def main():
                                  "h2d_bytes_per_step": int(s8.h2d_bytes), "d2h_bytes_per_step": int(s8.d2h_bytes),
                                  "call": "fg_render_rgb8 (host u8 RGB in/out, colour fused on device)"}
     else:
-        pin_in = torch.from_numpy(np.stack(lam_host)).pin_memory()
+        # each rank uploads only the lambda rows its band can see: band / zoom +- (max |offset| + rm) plus slack
+        reach = float(np.abs(d.offsets_input[:, 1]).max()) + float(d.rm) + 2.0
+        in_r0 = max(0, int(np.floor(rb / wl["zoom"] - reach)))
+        in_r1 = min(wl["h"], int(np.ceil(re / wl["zoom"] + reach)) + 1)
+        pin_in = torch.from_numpy(np.stack(lam_host)[:, in_r0:in_r1, :].copy()).pin_memory()
         pin_out = torch.empty((out_h, planes, out_w), dtype=torch.float32).pin_memory() if rank == 0 else None
         with torch.cuda.stream(stream):
             def step_e2e():
-                d_lam.copy_(pin_in, non_blocking=True)
+                d_lam[:, in_r0:in_r1, :].copy_(pin_in, non_blocking=True)
                 full = step_device()
                 if rank == 0:
                     pin_out.copy_(full, non_blocking=True)
@@ -351,7 +355,7 @@ def main():
         e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
                "h2d_bytes_per_step": int(pin_in.numel() * 4), "d2h_bytes_per_step": int(planes * out_w * out_h * 4),
                "ms_per_step": e2e_ms,
-               "call": "per rank: pinned H2D of the lambda planes + band render + NCCL band gather; rank 0: D2H of the image"}
+               "call": "per rank: pinned H2D of the lambda rows its band sees + band render + NCCL band gather; rank 0: D2H of the image"}
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")

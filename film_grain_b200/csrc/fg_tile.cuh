@@ -16,7 +16,10 @@
 //     G[pos] = (cx, cy); a sample's candidates in one cell row are one contiguous range;
 //   * evaluation: lane = output column, warp = sample subset; the per-(column,sample) cell range
 //     and the per-(row,sample) cell-row range are computed ONCE (IEEE division, exactly the
-//     reference's expression) and reused across the rows / columns they do not depend on.
+//     reference's expression) and reused across the rows / columns they do not depend on.  Per
+//     cell row a sample runs FG_TILE_USLOTS straight-line distance tests folded into a running
+//     minimum (one compare per sample), then an early-exit remainder loop; two samples advance
+//     together so their shared-memory loads overlap.
 //
 // Anything the fast path cannot hold (lambda' >= 12 -> rejection branch, window or grain ring
 // overflow, log-normal radii, exotic geometry) is appended to a fallback list and rendered by the
@@ -133,7 +136,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     float2* G = (float2*)(smem + cfg.off_G);
     uint16_t* list = (uint16_t*)(smem + cfg.off_list);
     uint16_t* E = (uint16_t*)(smem + cfg.off_E);
-    uint32_t* cntA = (uint32_t*)(smem + cfg.off_cnt);  // [64] counts, [64..128] exclusive offsets, [128] total
+    uint32_t* cntA = (uint32_t*)(smem + cfg.off_cnt);  // [FG_TILE_NE] non-empty counts per (iteration, warp)
     uint32_t* wtot = (uint32_t*)(smem + cfg.off_wtot); // [NW] warp totals, [NW] general-path flag
     uint32_t* pcount = (uint32_t*)(smem + cfg.off_pcount);
     float2* wpair = (float2*)(smem + cfg.off_wpair);
