@@ -310,8 +310,6 @@ void fg_context_destroy(fg_ctx* ctx) {
         for (DevBuf* b : {&ctx->lambda, &ctx->out, &ctx->offsets, &ctx->bits, &ctx->counts, &ctx->scan_out, &ctx->scan_tmp,
                           &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut})
             release(*b);
-        if (ctx->pin_in.p) cudaFreeHost(ctx->pin_in.p);
-        if (ctx->pin_out.p) cudaFreeHost(ctx->pin_out.p);
         for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         cudaGetLastError();

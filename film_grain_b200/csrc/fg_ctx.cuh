@@ -21,11 +21,6 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-struct HostBuf { // pinned staging
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
 } // namespace
 
 struct fg_ctx {
@@ -40,7 +35,6 @@ struct fg_ctx {
     size_t smem_optin = 0;
     // pools
     DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, rgb_in, rgb_out, chroma, lut;
-    HostBuf pin_in, pin_out;
     bool tables_ready = false;
     uint32_t fb_count_host = 0; // tiled path: fallback-list length of the last render (valid after a stream sync)
     bool fb_pending = false;
@@ -98,15 +92,6 @@ int ensure(fg_ctx* ctx, DevBuf& b, size_t bytes) {
     }
     if (e != cudaSuccess) { b.p = nullptr; return map_cuda_error(ctx, e, "cudaMalloc"); }
     b.cap = want;
-    return FG_OK;
-}
-
-int ensure_pinned(fg_ctx* ctx, HostBuf& b, size_t bytes) {
-    if (bytes <= b.cap) return FG_OK;
-    if (b.p) { cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
-    cudaError_t e = cudaMallocHost(&b.p, bytes);
-    if (e != cudaSuccess) { b.p = nullptr; return map_cuda_error(ctx, e, "cudaMallocHost"); }
-    b.cap = bytes;
     return FG_OK;
 }
 

@@ -274,3 +274,63 @@ def test_cancel_flag(ctx):
     finally:
         ctx.set_cancel_flag(None)
     ctx.render_pixelwise(fg_params_from(p, d), lam, off_in)
+
+
+def test_full_size_config2_plane_properties(ctx):
+    """BASELINE.json configs[1] at full size (3840x2160, r=0.1, N=256, one colour plane): the strip
+    kernel against (a) the oracle on two 6-row bands, (b) the independent direct kernel on three
+    48-row bands (top edge, middle, bottom edge), (c) the Boolean-model identity E[pixel] = u on the image mean."""
+    w, h, n = 3840, 2160, 256
+    p = O.make_params(radius=0.1, n_samples=n, algo=O.ALGO_PIXEL, seed=5489)
+    d, off, off_in = O.derive_common(p, w, h)
+    img = noise_u8(w, h)  # the bench input
+    lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
+    full = ctx.render_pixelwise(fg_params_from(p, d, path=2), lam, off_in)
+    st = ctx.stats()
+    assert st.tiles_total > 0 and st.tiles_fallback == 0
+    for a, b in ((0, 6), (1237, 1243)):
+        ref = O.render_pixelwise(lam, p, d, off_in, a, b)
+        assert np.array_equal(ref[a:b], full[a:b])
+    direct = np.full_like(full, -1.0)
+    for a, b in ((0, 48), (1050, 1098), (2112, 2160)):
+        ctx.render_pixelwise(fg_params_from(p, d, path=1, rows=(a, b)), lam, off_in, out=direct)
+        assert np.array_equal(direct[a:b], full[a:b])
+    # iid 8-bit noise is the worst case for the identity: grains of radius r straddle pixels of very
+    # different lambda and 1-exp(-x) is concave, so coverage is biased upwards (Jensen) by ~0.013;
+    # the image mean still has to land next to the input mean
+    u = img[:, :, 0].astype(np.float64) / 255.0
+    assert 0.0 <= full.mean() - u.mean() < 0.03
+
+
+def test_full_size_config4_band(ctx):
+    """BASELINE.json configs[3] geometry (2048^2 input, zoom 4, r=0.05, N=64): one 96-row output band,
+    strip kernel == direct kernel, and == the oracle on 4 rows."""
+    w = h = 2048
+    p = O.make_params(radius=0.05, n_samples=64, zoom=4.0, algo=O.ALGO_PIXEL, seed=5489)
+    d, off, off_in = O.derive_common(p, w, h)
+    assert (d.output_width, d.output_height) == (8192, 8192)
+    lam = lambda_from_u8(noise_u8(w, h)[:, :, 1], d.inv_e_pi_r2)
+    a, b = 4000, 4096
+    tiled = np.zeros((8192, 8192), np.float32)
+    direct = np.zeros((8192, 8192), np.float32)
+    ctx.render_pixelwise(fg_params_from(p, d, path=2, rows=(a, b)), lam, off_in, out=tiled)
+    ctx.render_pixelwise(fg_params_from(p, d, path=1, rows=(a, b)), lam, off_in, out=direct)
+    assert np.array_equal(tiled[a:b], direct[a:b])
+    ref = O.render_pixelwise(lam, p, d, off_in, a, a + 4)
+    assert np.array_equal(ref[a:a + 4], tiled[a:a + 4])
+
+
+def test_full_size_config3_grainwise_crop_consistency(ctx):
+    """BASELINE.json configs[2] parameters (grain-wise, r=0.5, N=128): a 1024x1024 render equals the
+    oracle on the same input (the oracle needs ~10 s for this size), and a band split reproduces it."""
+    w = h = 1024
+    p = O.make_params(radius=0.5, n_samples=128, algo=O.ALGO_GRAIN, seed=5489)
+    d, off, off_in = O.derive_common(p, w, h)
+    lam = lambda_from_u8(noise_u8(w, h)[:, :, 0], d.inv_e_pi_r2)
+    got = ctx.render_grainwise(fg_params_from(p, d), lam, off)
+    ref = O.render_grainwise(lam, p, d, off)
+    assert np.array_equal(ref, got)
+    banded = np.zeros_like(got)
+    for a, b in ((0, 300), (300, 301), (301, 1024)):
+        ctx.render_grainwise(fg_params_from(p, d, rows=(a, b)), lam, off, out=banded)
+    assert np.array_equal(banded, got)
