@@ -359,12 +359,18 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                 }
                 if (lane == 31) wtot[warp] = incl;
                 __syncthreads();
-                uint32_t boff = 0, total = 0;
+                // warp totals -> this warp's offset and the pass total: one shuffle scan per warp
+                uint32_t boff, total;
+                {
+                    const uint32_t v = (lane < FG_TILE_WARPS) ? wtot[lane] : 0u;
+                    uint32_t wincl = v;
 #pragma unroll
-                for (int w = 0; w < FG_TILE_WARPS; ++w) {
-                    uint32_t v = wtot[w];
-                    if (w < warp) boff += v;
-                    total += v;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, wincl, d);
+                        if (lane >= d) wincl += u;
+                    }
+                    total = __shfl_sync(0xFFFFFFFFu, wincl, FG_TILE_WARPS - 1);
+                    boff = __shfl_sync(0xFFFFFFFFu, wincl - v, warp);
                 }
                 if (used + total > (uint32_t)cfg.GCAP) { // uniform: grain ring overflow
                     if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
