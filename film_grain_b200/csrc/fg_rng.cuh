@@ -182,8 +182,10 @@ __device__ inline uint32_t poisson_f64(Xoshiro& r, double lambda) {
 }
 
 // ziggurat tables of rand_distr 0.4.3 (257 entries each), filled once per context
-__constant__ double kZigX[257];
-__constant__ double kZigF[257];
+// (global, read through the read-only path: lanes index different layers, which would serialise in
+// the constant cache)
+__device__ double kZigX[257];
+__device__ double kZigF[257];
 #define FG_ZIG_R 3.654152885361008796
 
 // rand_distr 0.4.3 StandardNormal f64 (ziggurat, symmetric)
@@ -192,7 +194,7 @@ __device__ inline double standard_normal(Xoshiro& r) {
         uint64_t bits = next_u64(r);
         int i = (int)(bits & 0xff);
         double u = __dsub_rn(__longlong_as_double((long long)((bits >> 12) | 0x4000000000000000ULL)), 3.0);
-        double xi = kZigX[i], xi1 = kZigX[i + 1];
+        double xi = __ldg(&kZigX[i]), xi1 = __ldg(&kZigX[i + 1]);
         double x = __dmul_rn(u, xi);
         if (fabs(x) < xi1) return x;
         if (i == 0) { // tail
@@ -205,7 +207,7 @@ __device__ inline double standard_normal(Xoshiro& r) {
             }
             return (u < 0.0) ? __dsub_rn(tx, FG_ZIG_R) : __dsub_rn(FG_ZIG_R, tx);
         }
-        double f0 = kZigF[i], f1 = kZigF[i + 1];
+        double f0 = __ldg(&kZigF[i]), f1 = __ldg(&kZigF[i + 1]);
         double lhs = __dadd_rn(f1, __dmul_rn(__dsub_rn(f0, f1), standard_f64(r)));
         double pdf = exp(__ddiv_rn(__dmul_rn(-x, x), 2.0));
         if (lhs < pdf) return x;

@@ -66,9 +66,9 @@ struct TileCfg {
     int TH, SEG;          // pixel rows per step, rows per segment
     int CWB, RH, PS;      // cell-column bound, ring rows, P row stride (u16 elements)
     int R;                // cell rows per generation group
-    int GCAP;             // grain ring capacity (power of two <= 65536)
+    int GCAP;             // grain ring capacity (<= 65535 entries; P holds ring indices as u16)
     int n_strips, n_segs;
-    uint32_t off_col, off_P, off_G, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, total;
+    uint32_t off_col, off_P, off_G, off_R2, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, total;
 };
 
 #ifndef FG_TILE_WARPS
@@ -110,6 +110,11 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
@@ -124,7 +129,7 @@ __device__ __noinline__ uint32_t col_range_packed(float xg, float rm, float delt
     return (uint32_t)(2 * (i0 - i_lo)) | ((uint32_t)(2 * (i1 - i_lo + 1)) << 16);
 }
 
-template <int SPWC>
+template <int SPWC, bool LOGN>
 __global__ void __launch_bounds__(FG_TILE_THREADS, 1)
 k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restrict__ e_planes, size_t in_stride,
                   const float2* __restrict__ offsets_input, float* __restrict__ out, size_t out_stride,
@@ -134,6 +139,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     ColInfo* colT = (ColInfo*)(smem + cfg.off_col);
     uint16_t* P = (uint16_t*)(smem + cfg.off_P);
     float2* G = (float2*)(smem + cfg.off_G);
+    float* R2 = (float*)(smem + cfg.off_R2); // LOGN only: squared clamped radius per grain (-1: never covers)
     uint16_t* list = (uint16_t*)(smem + cfg.off_list);
     uint16_t* E = (uint16_t*)(smem + cfg.off_E);
     uint32_t* cntA = (uint32_t*)(smem + cfg.off_cnt);  // [FG_TILE_NE] non-empty counts per (iteration, warp)
@@ -157,8 +163,8 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     float* outp = out + out_stride * plane;
     const float rm = c.rad.rm, delta = c.delta;
     const float r2 = __fmul_rn(c.rad.mean_linear > rm ? rm : c.rad.mean_linear, c.rad.mean_linear > rm ? rm : c.rad.mean_linear);
-    const bool radius_ok = (c.rad.mean_linear > rm ? rm : c.rad.mean_linear) > 0.0f; // radius <= 0: grains never cover
-    const int GM = cfg.GCAP - 1;
+    const bool radius_ok = LOGN || (c.rad.mean_linear > rm ? rm : c.rad.mean_linear) > 0.0f; // const radius <= 0: grains never cover
+    const uint32_t GC = (uint32_t)cfg.GCAP;
 
     // ---- horizontal cell window of the strip (monotone in x and in the offset) ----
     const float bx0 = __fmul_rn(__fadd_rn((float)X0, 0.5f), c.inv_zoom);
@@ -219,7 +225,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     __syncthreads();
 
     // ---- ring state (uniform across the CTA) ----
-    uint32_t head = 0;            // absolute grain counter; ring position = head & GM; P holds (u16)head
+    uint32_t head = 0;            // ring index of the next grain, in [0, GC); P holds ring indices
     int j_gen = 0, rr_gen = 0;    // next cell row to generate and its ring row
     int j_lo_prev = 0, rr_lo = 0; // oldest live cell row and its ring row
     bool first = true;
@@ -247,7 +253,11 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
             if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
             return;
         }
-        uint32_t used = (j_lo < j_gen) ? ((head - (uint32_t)P[rr_lo * PS]) & 0xFFFFu) : 0u;
+        uint32_t used = 0u; // grains of the live rows: ring distance from the oldest live row's first grain
+        if (j_lo < j_gen) {
+            const uint32_t tail = P[rr_lo * PS];
+            used = head - tail + (head < tail ? GC : 0u);
+        }
 
         // =================== generation: cell rows j_gen .. j_hi in groups of <= R rows ===================
         while (j_gen <= j_hi) {
@@ -372,22 +382,30 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                     total = __shfl_sync(0xFFFFFFFFu, wincl, FG_TILE_WARPS - 1);
                     boff = __shfl_sync(0xFFFFFFFFu, wincl - v, warp);
                 }
-                if (used + total > (uint32_t)cfg.GCAP) { // uniform: grain ring overflow
+                if (used + total >= GC) { // uniform: grain ring overflow (== GC would alias an empty ring)
                     if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
                     return;
                 }
                 if (t < M) {
                     uint32_t pos = head + boff + (incl - q);
+                    if (pos >= GC) pos -= GC;
                     E[t] = (uint16_t)pos;
                     for (uint32_t g = 0; g < q; ++g) {
                         float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
                         float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
-                        const uint32_t gi = (pos + g) & GM;
-                        G[gi] = make_float2(cx, cy);
-                        if (gi < FG_TILE_GPAD) G[cfg.GCAP + gi] = make_float2(cx, cy); // mirror: reads never wrap
+                        G[pos] = make_float2(cx, cy);
+                        if (pos < FG_TILE_GPAD) G[GC + pos] = make_float2(cx, cy); // mirror: unrolled reads never wrap
+                        if (LOGN) { // RadiusProfile::sample + clamp (src/model.rs:137-148, src/pixelwise.rs:89-95)
+                            const float radius = radius_sample_clamped(c.rad, rng);
+                            const float rr2 = radius > 0.0f ? __fmul_rn(radius, radius) : -1.0f;
+                            R2[pos] = rr2;
+                            if (pos < FG_TILE_GPAD) R2[GC + pos] = rr2;
+                        }
+                        if (++pos == GC) pos = 0;
                     }
                 }
                 head += total;
+                if (head >= GC) head -= GC;
                 used += total;
                 __syncthreads(); // wtot reuse + E/G visible
             }
@@ -440,6 +458,49 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
             if (xvalid && radius_ok) {
                 const uint32_t Ps = (uint32_t)__cvta_generic_to_shared(P), Gs = (uint32_t)__cvta_generic_to_shared(G);
                 const uint32_t PS2 = (uint32_t)PS * 2u, RHPS2 = (uint32_t)RH * PS2;
+                if (LOGN) {
+                    // per-grain radii: one sample at a time, per cell row FG_TILE_USLOTS predicated tests
+                    // against the grain's own r^2, then an early-exit remainder loop
+                    const uint32_t Rs = (uint32_t)__cvta_generic_to_shared(R2);
+                    for (int yl = 0; yl < th; ++yl) {
+                        uint32_t cnt = 0;
+#pragma unroll
+                        for (int s = 0; s < SPWC; ++s) {
+                            const float2 pd = wp[s * th + yl];
+                            const uint32_t jp = __float_as_uint(pd.y);
+                            const uint32_t a2 = ip_r[s] & 0xFFFFu, b2 = ip_r[s] >> 16;
+                            const uint32_t nrow = (a2 != b2) ? (jp >> 24) : 0u;
+                            uint32_t off = Ps + (jp & 0xFFFFFFu);
+                            const float xg = xg_r[s], yg = pd.x;
+                            uint32_t covered = 0;
+#pragma unroll 1
+                            for (uint32_t r = 0; r < nrow && !covered; ++r) {
+                                const uint32_t s16 = lds_u16(off + a2), e16 = lds_u16(off + b2);
+                                const uint32_t n = e16 - s16 + (e16 < s16 ? GC : 0u);
+#pragma unroll
+                                for (int u = 0; u < FG_TILE_USLOTS; ++u) {
+                                    const float2 gr = lds_f32x2(Gs + (s16 + u) * 8u); // past n: stale, in-bounds (mirror pad)
+                                    const float rr2 = lds_f32(Rs + (s16 + u) * 4u);
+                                    const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
+                                    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    covered |= ((uint32_t)u < n && d2 <= rr2) ? 1u : 0u;
+                                }
+                                for (uint32_t u = FG_TILE_USLOTS; u < n && !covered; ++u) {
+                                    uint32_t gi = s16 + u;
+                                    if (gi >= GC) gi -= GC;
+                                    const float2 gr = lds_f32x2(Gs + gi * 8u);
+                                    const float rr2 = lds_f32(Rs + gi * 4u);
+                                    const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
+                                    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= rr2) covered = 1u;
+                                }
+                                off += PS2;
+                                if (off >= Ps + RHPS2) off = Ps;
+                            }
+                            cnt += covered;
+                        }
+                        if (cnt) atomicAdd(&pcount[yl * 32 + lane], cnt);
+                    }
+                } else
                 for (int yl = 0; yl < th; ++yl) {
                     uint32_t cnt = 0;
                     // two samples (A, B) advance through their cell rows together: their shared-memory
@@ -462,8 +523,8 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                             const uint32_t bA = (r < nrowA) ? b2A : a2A, bB = (r < nrowB) ? b2B : a2B;
                             const uint32_t sA = lds_u16(offA + a2A), eA = lds_u16(offA + bA);
                             const uint32_t sB = lds_u16(offB + a2B), eB = lds_u16(offB + bB);
-                            const uint32_t nA = (eA - sA) & 0xFFFFu, nB = (eB - sB) & 0xFFFFu;
-                            const uint32_t gaA = Gs + (sA & GM) * 8u, gaB = Gs + (sB & GM) * 8u;
+                            const uint32_t nA = eA - sA + (eA < sA ? GC : 0u), nB = eB - sB + (eB < sB ? GC : 0u);
+                            const uint32_t gaA = Gs + sA * 8u, gaB = Gs + sB * 8u;
                             float2 gA[FG_TILE_USLOTS], gB[FG_TILE_USLOTS];
 #pragma unroll
                             for (int u = 0; u < FG_TILE_USLOTS; ++u) gA[u] = lds_f32x2(gaA + 8u * u); // past n: stale, in-bounds
@@ -481,7 +542,9 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                             if (nA > FG_TILE_USLOTS && !(dminA <= r2)) { // remainder: exits on the first hit
                                 uint32_t u = FG_TILE_USLOTS;
                                 do {
-                                    const float2 gr = lds_f32x2(Gs + ((sA + u) & GM) * 8u);
+                                    uint32_t gi = sA + u;
+                                    if (gi >= GC) gi -= GC;
+                                    const float2 gr = lds_f32x2(Gs + gi * 8u);
                                     const float dx = __fsub_rn(xgA, gr.x), dy = __fsub_rn(ygA, gr.y);
                                     const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
                                     if (d2 <= r2) { dminA = d2; break; }
@@ -490,7 +553,9 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                             if (nB > FG_TILE_USLOTS && !(dminB <= r2)) {
                                 uint32_t u = FG_TILE_USLOTS;
                                 do {
-                                    const float2 gr = lds_f32x2(Gs + ((sB + u) & GM) * 8u);
+                                    uint32_t gi = sB + u;
+                                    if (gi >= GC) gi -= GC;
+                                    const float2 gr = lds_f32x2(Gs + gi * 8u);
                                     const float dx = __fsub_rn(xgB, gr.x), dy = __fsub_rn(ygB, gr.y);
                                     const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
                                     if (d2 <= r2) { dminB = d2; break; }
@@ -531,7 +596,6 @@ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes) {
     TilePlan pl{};
     pl.ok = false;
-    if (c.rad.lognorm) return pl;                       // per-grain radii: direct kernel (for now)
     if (p->n_samples > (1u << 20)) return pl;
     const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
     const double ox = (double)c.off_max_x - (double)c.off_min_x, oy = (double)c.off_max_y - (double)c.off_min_y;
@@ -544,36 +608,43 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     const int spwc = p->n_samples <= 4u * FG_TILE_WARPS ? 4 : (p->n_samples <= 8u * FG_TILE_WARPS ? 8 : FG_TILE_SPW_MAX);
     const int band = c.row_end - c.row_begin;
     const size_t smem_max = ctx->smem_optin;
-    // pass 0 insists that the grain ring holds the window at a plausible density (0.45 grains per
-    // cell; iid-uniform 8-bit input averages 1/pi); pass 1 takes anything that fits -- denser
-    // content overflows into the fallback list at run time.
+    const uint32_t bpg = c.rad.lognorm ? 12u : 8u;      // bytes per grain: (cx, cy) [+ r^2]
+    // Largest step height whose window fits; the grain ring takes all remaining shared memory.
+    // pass 0 insists that the ring holds the window at a plausible density (0.45 grains per cell;
+    // iid-uniform 8-bit input averages 1/pi); pass 1 takes anything that fits -- denser content
+    // overflows into the fallback list at run time.
     for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
-        for (int gcap = 16384; gcap >= 2048 && !pl.ok; gcap >>= 1) {
-            static const int th_candidates[] = {32, 24, 16, 12, 8, 6, 4, 3, 2, 1};
-            for (int TH : th_candidates) {
-                if (pl.ok) break;
-                if (TH > 1 && TH > 2 * band) continue;
-                const double rhb = ((TH - 1) * inv_zoom + oy + 2.0 * rm) / delta + 4.0;
-                if (!(rhb < 30000.0)) continue;
-                const int RH = (int)rhb;
-                TileCfg g{};
-                g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R; g.GCAP = gcap;
-                uint32_t off = 0;
-                g.off_col = off; off = align_up(off + (uint32_t)CWB * 16u, 16);
-                g.off_G = off; off = align_up(off + (uint32_t)(gcap + FG_TILE_GPAD) * 8u, 16);
-                g.off_P = off; off = align_up(off + (uint32_t)RH * PS * 2u, 16);
-                g.off_list = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
-                g.off_E = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
-                g.off_cnt = off; off = align_up(off + (uint32_t)(FG_TILE_NE + 8) * 4u, 16);
-                g.off_wtot = off; off = align_up(off + (uint32_t)(FG_TILE_WARPS + 4) * 4u, 16);
-                g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
-                g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
-                g.total = off;
-                if (off > smem_max) continue;
-                if (pass == 0 && (double)gcap < 0.45 * (double)RH * (double)CWB) continue;
-                pl.cfg = g;
-                pl.ok = true;
-            }
+        static const int th_candidates[] = {32, 24, 16, 12, 8, 6, 4, 3, 2, 1};
+        for (int TH : th_candidates) {
+            if (pl.ok) break;
+            if (TH > 1 && TH > 2 * band) continue;
+            const double rhb = ((TH - 1) * inv_zoom + oy + 2.0 * rm) / delta + 4.0;
+            if (!(rhb < 30000.0)) continue;
+            const int RH = (int)rhb;
+            TileCfg g{};
+            g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R;
+            uint32_t off = 0;
+            g.off_col = off; off = align_up(off + (uint32_t)CWB * 16u, 16);
+            g.off_P = off; off = align_up(off + (uint32_t)RH * PS * 2u, 16);
+            g.off_list = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
+            g.off_E = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
+            g.off_cnt = off; off = align_up(off + (uint32_t)(FG_TILE_NE + 8) * 4u, 16);
+            g.off_wtot = off; off = align_up(off + (uint32_t)(FG_TILE_WARPS + 4) * 4u, 16);
+            g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
+            g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
+            if ((size_t)off + 64 + (size_t)bpg * (2048 + FG_TILE_GPAD) > smem_max) continue;
+            uint32_t gcap = (uint32_t)((smem_max - off - 64) / bpg) - FG_TILE_GPAD;
+            gcap = std::min<uint32_t>(gcap / 64 * 64, 65472u);
+            if (gcap < 2048) continue;
+            if (pass == 0 && (double)gcap < 0.45 * (double)RH * (double)CWB) continue;
+            g.GCAP = (int)gcap;
+            g.off_G = off; off = align_up(off + (gcap + FG_TILE_GPAD) * 8u, 16);
+            g.off_R2 = off;
+            if (c.rad.lognorm) off = align_up(off + (gcap + FG_TILE_GPAD) * 4u, 16);
+            g.total = off;
+            if (off > smem_max) continue;
+            pl.cfg = g;
+            pl.ok = true;
         }
     }
     if (!pl.ok) return pl;
@@ -608,9 +679,12 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
 int tile_setup(fg_ctx* ctx) {
     cudaError_t e;
     const int smem = (int)ctx->smem_optin;
-    if ((e = cudaFuncSetAttribute(k_pixelwise_strip<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<FG_TILE_SPW_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_pixelwise_strip<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<FG_TILE_SPW_MAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_strip<FG_TILE_SPW_MAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_strip)");
     return FG_OK;
 }
@@ -638,11 +712,23 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
     FG_CUDA(ctx, cudaGetLastError());
     const float2* off = (const float2*)d_offsets;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-    switch (pl.spwc) {
-    case 4: k_pixelwise_strip<4><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
-    case 8: k_pixelwise_strip<8><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
-    default: k_pixelwise_strip<FG_TILE_SPW_MAX><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c); break;
+#define FG_LAUNCH_STRIP(SP, LG)                                                                                   \
+    k_pixelwise_strip<SP, LG><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, \
+                                                                       d_fblist, d_fbcount, units, g, c)
+    if (c.rad.lognorm) {
+        switch (pl.spwc) {
+        case 4: FG_LAUNCH_STRIP(4, true); break;
+        case 8: FG_LAUNCH_STRIP(8, true); break;
+        default: FG_LAUNCH_STRIP(FG_TILE_SPW_MAX, true); break;
+        }
+    } else {
+        switch (pl.spwc) {
+        case 4: FG_LAUNCH_STRIP(4, false); break;
+        case 8: FG_LAUNCH_STRIP(8, false); break;
+        default: FG_LAUNCH_STRIP(FG_TILE_SPW_MAX, false); break;
+        }
     }
+#undef FG_LAUNCH_STRIP
     FG_CUDA(ctx, cudaGetLastError());
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
     const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);

@@ -94,6 +94,10 @@ PIXEL_CASES = [
     ("strips_N300_two_chunks", 34, 40, dict(radius=0.1, n_samples=300)),
     ("strips_r0.3_sigma2", 90, 80, dict(radius=0.3, n_samples=16, sigma_px=2.0)),
     ("strips_cell_half_rm", 60, 60, dict(radius=0.1, n_samples=8, cell_delta=0.05)),
+    # log-normal radii inside the strip kernel (per-grain r^2 ring)
+    ("strips_lognorm_ratio0.5_noise", 150, 110, dict(radius=0.1, radius_dist=O.DIST_LOGNORM, radius_stddev=0.05, n_samples=24)),
+    ("strips_lognorm_ratio1_zoom2_noise", 60, 50, dict(radius=0.2, radius_dist=O.DIST_LOGNORM, radius_stddev=0.2, n_samples=12, zoom=2.0)),
+    ("strips_lognorm_sigma0", 64, 40, dict(radius=0.15, radius_dist=O.DIST_LOGNORM, radius_stddev=0.0, n_samples=8)),
 ]
 
 
