@@ -5,8 +5,8 @@ read our numbers next to its own rows.
 
 Differences from the reference tool, on purpose: it times whole process launches (PNG decode/encode
 and start-up included); here `runtime_seconds` is the in-process time of `render_with_input_image`
-(host mirror: load, lambda, device integrator, store -- the same data flow as lib.rs:134-173) on a
-decoded 8-bit image, median of `--repeats` calls after one warm-up.  Inputs are the tool's synthetic
+(8-bit image in, 8-bit image out; load / lambda / store fused on the device, or the reference's
+host data flow of lib.rs:134-173 with --host-color) on a decoded image, median of `--repeats` calls after one warm-up.  Inputs are the tool's synthetic
 intensity fields (constant / step / ramp / natural, :147-177).
 
 usage (on a GPU box):  python tools/bench_sweep_b200.py --out gpurun_out/b200_benchmark_results.csv
@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--patterns", nargs="+", default=["constant", "ramp", "natural"])
     ap.add_argument("--algos", nargs="+", default=["pixel", "grain"])
     ap.add_argument("--repeats", type=int, default=3)
+    ap.add_argument("--host-color", action="store_true", help="host load/lambda/store (the reference data flow) instead of the fused device path")
     ap.add_argument("--budget-evals", type=float, default=6e9, help="skip configs above this many sample evaluations")
     args = ap.parse_args()
 
@@ -90,12 +91,12 @@ def main():
                                                          radius_dist=H.RadiusDist.Lognorm if ratio > 0 else H.RadiusDist.Const,
                                                          radius_stddev=mu * ratio, color_mode=H.ColorMode.Luma)
                                     p = pb.build()
-                                    H.render_with_input_image(img, p)  # warm-up
+                                    H.render_with_input_image(img, p, fused=not args.host_color)  # warm-up
                                     ts = []
                                     for rep in range(args.repeats):
                                         p = H.ParamsBuilder(**{**pb.__dict__, "seed": 5489 + rep}).build()
                                         t0 = time.perf_counter()
-                                        H.render_with_input_image(img, p)
+                                        H.render_with_input_image(img, p, fused=not args.host_color)
                                         ts.append(time.perf_counter() - t0)
                                     w.writerow({"algorithm": algo, "device": "b200", "thread_mode": "gpu", "m": m, "n": m, "N": N,
                                                 "mu_r": fmt(mu), "sigma_r_ratio": fmt(ratio), "s": s, "intensity_pattern": pattern,
