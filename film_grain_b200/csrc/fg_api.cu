@@ -308,7 +308,7 @@ void fg_context_destroy(fg_ctx* ctx) {
         ScopedDevice dev(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         for (DevBuf* b : {&ctx->lambda, &ctx->out, &ctx->offsets, &ctx->bits, &ctx->counts, &ctx->scan_out, &ctx->scan_tmp,
-                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut})
+                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->bitmap, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut})
             release(*b);
         for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -50,13 +50,61 @@ __global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ la
                     th = (uint64_t)(e * 9007199254740992.0);
                 } else {
                     th = FG_THR_GENERAL;
+                    e = -1.0; // the dense phase recognises "needs the general path" by e < 0
                 }
             }
         } else if (lam != lam) {
             th = FG_THR_GENERAL;
+            e = -1.0;
         }
         thr[t] = th;
         ev[t] = e;
+    }
+}
+
+// First-draw bitmap: one bit per Boolean-model cell and colour plane, 1 = "the cell's first Knuth draw
+// exceeds its threshold", i.e. the cell holds at least one grain (or needs the general path).  The
+// hash, the four PCG seed words and the first xoshiro draw depend only on (seed, i, j): they are
+// computed ONCE per cell here and compared against every plane's threshold, instead of once per plane
+// and per strip window inside the strip kernel.  grid (ceil(rows/FG_BM_ROWS), ceil(cols/256)), block 256,
+// one thread per cell column; each warp
+// stores one aligned 32-bit word per plane.
+#define FG_BM_ROWS 16 // cell rows per thread in k_first_draw_bitmap (amortises the column half of the hash)
+__global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __restrict__ thr_planes, size_t in_stride,
+                                                            int n_planes, uint32_t* __restrict__ bm, size_t bm_plane_words,
+                                                            int i0, int j0, int cols, int rows, uint32_t pitchw, RenderConsts c) {
+    const int col = blockIdx.y * 256 + threadIdx.x;
+    const int row0 = blockIdx.x * FG_BM_ROWS;
+    const bool valid = col < cols;
+    const bool store = (threadIdx.x & 31) == 0 && col < (int)(pitchw * 32u);
+    const int i = i0 + col;
+    const uint64_t hcol = mix3_col(c.seed_cell, i);
+    const int ix = min(max(floor_i32(__fmul_rn(__int2float_rn(i), c.delta)), 0), c.in_w - 1);
+#pragma unroll 4
+    for (int rr = 0; rr < FG_BM_ROWS; ++rr) {
+        const int row = row0 + rr;
+        if (row >= rows) break; // uniform
+        const int j = j0 + row;
+        uint64_t m1 = 0;
+        size_t pix = 0;
+        if (valid) {
+            const uint64_t h = mix3_row(hcol, j);
+            uint64_t s0, s3;
+            if (c.seeding == 0) { s0 = pcg_word_pair<0>(h); s3 = pcg_word_pair<3>(h); }
+            else { Xoshiro t; seed_splitmix(t, h); s0 = t.s0; s3 = t.s3; }
+            m1 = (rotl64(s0 + s3, 23) + s0) >> 11;
+            const int iy = min(max(floor_i32(__fmul_rn(__int2float_rn(j), c.delta)), 0), c.in_h - 1);
+            pix = (size_t)iy * c.in_w + ix;
+        }
+        for (int pl = 0; pl < n_planes; ++pl) {
+            bool ne = false;
+            if (valid) {
+                const uint64_t th64 = __ldg(thr_planes + in_stride * pl + pix);
+                ne = (th64 == FG_THR_GENERAL) || (m1 > th64);
+            }
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne);
+            if (store) bm[bm_plane_words * pl + (size_t)row * pitchw + (col >> 5)] = m;
+        }
     }
 }
 
@@ -68,6 +116,9 @@ struct TileCfg {
     int R;                // cell rows per generation group
     int GCAP;             // grain ring capacity (<= 65535 entries; P holds ring indices as u16)
     int n_strips, n_segs;
+    int bm_i0, bm_j0;     // first cell column / row of the first-draw bitmap
+    int bm_cols, bm_rows; // its extent in cells
+    uint32_t bm_pitchw;   // 32-bit words per bitmap row
     uint32_t off_col, off_P, off_G, off_R2, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, total;
 };
 
@@ -131,7 +182,7 @@ __device__ __noinline__ uint32_t col_range_packed(float xg, float rm, float delt
 
 template <int SPWC, bool LOGN>
 __global__ void __launch_bounds__(FG_TILE_THREADS, 1)
-k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restrict__ e_planes, size_t in_stride,
+k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words, const double* __restrict__ e_planes, size_t in_stride,
                   const float2* __restrict__ offsets_input, float* __restrict__ out, size_t out_stride,
                   TileRef* __restrict__ fb_list, uint32_t* __restrict__ fb_count, uint32_t fb_cap, TileCfg cfg,
                   RenderConsts c) {
@@ -158,7 +209,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     if (X0 >= c.out_w || Y0 >= c.row_end) return;
     const int X1 = min(X0 + 32, c.out_w) - 1;      // inclusive
     const int Y1 = min(Y0 + cfg.SEG, c.row_end);   // exclusive
-    const uint64_t* thr = thr_planes + in_stride * plane;
+    const uint32_t* bm = bm_planes + bm_plane_words * plane;
     const double* ev = e_planes + in_stride * plane;
     float* outp = out + out_stride * plane;
     const float rm = c.rad.rm, delta = c.delta;
@@ -172,7 +223,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     const int i_lo = cell_lo(__fsub_rn(bx0, c.off_max_x), rm, delta);
     const int i_hi = cell_hi(__fsub_rn(bx1, c.off_min_x), rm, delta);
     const long long CWl = (long long)i_hi - (long long)i_lo + 1;
-    if (CWl < 1 || CWl > cfg.CWB) { // uniform
+    if (CWl < 1 || CWl > cfg.CWB || i_lo < cfg.bm_i0 || (long long)i_hi >= (long long)cfg.bm_i0 + cfg.bm_cols) { // uniform
         if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, Y0, X1 - X0 + 1, Y1 - Y0, plane);
         return;
     }
@@ -224,6 +275,24 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
     bool xk_loaded = false;
     __syncthreads();
 
+    // first-draw bitmap words of this thread's phase-A cells for the group starting at row jg
+    uint32_t bmw[FG_TILE_ITERS], bsh[FG_TILE_ITERS];
+#pragma unroll
+    for (int it = 0; it < FG_TILE_ITERS; ++it) { bmw[it] = 0u; bsh[it] = (uint32_t)(i_lo - cfg.bm_i0 + (rci[it] & 0xFFFF)) & 31u; }
+    int j_bm = INT_MIN; // group start row the words in bmw[] belong to
+    auto load_bm = [&](int jg) {
+        j_bm = jg;
+#pragma unroll
+        for (int it = 0; it < FG_TILE_ITERS; ++it) {
+            const int rc = rci[it];
+            const long long brow = (long long)jg - cfg.bm_j0 + (rc >> 16);
+            if (rc >= 0 && (rc & 0xFFFF) < CW && brow >= 0 && brow < cfg.bm_rows) {
+                const uint32_t bcol = (uint32_t)(i_lo - cfg.bm_i0 + (rc & 0xFFFF));
+                bmw[it] = __ldg(bm + (size_t)brow * cfg.bm_pitchw + (bcol >> 5));
+            }
+        }
+    };
+
     // ---- ring state (uniform across the CTA) ----
     uint32_t head = 0;            // ring index of the next grain, in [0, GC); P holds ring indices
     int j_gen = 0, rr_gen = 0;    // next cell row to generate and its ring row
@@ -239,7 +308,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
         const int j_lo = cell_lo(__fsub_rn(bya, c.off_max_y), rm, delta);
         const int j_hi = cell_hi(__fsub_rn(byb, c.off_min_y), rm, delta);
         const long long WH = (long long)j_hi - (long long)j_lo + 1;
-        bool fail = (WH < 1 || WH > RH);
+        bool fail = (WH < 1 || WH > RH || j_lo < cfg.bm_j0 || (long long)j_hi >= (long long)cfg.bm_j0 + cfg.bm_rows);
         if (!fail) {
             if (first) { j_gen = j_lo; rr_gen = 0; rr_lo = 0; first = false; }
             else {
@@ -262,42 +331,22 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
         // =================== generation: cell rows j_gen .. j_hi in groups of <= R rows ===================
         while (j_gen <= j_hi) {
             const int nr = min(r_cur, j_hi - j_gen + 1);
+            if (j_bm != j_gen) load_bm(j_gen); // first group, or the window jumped (uniform)
             // ---- phase A: first-draw filter on every cell of the group (4 independent hash chains
             //      per thread are issued back to back before the ballots) ----
             uint32_t masks[FG_TILE_ITERS];
-            bool ne[FG_TILE_ITERS];
-            bool general = false;
 #pragma unroll
             for (int it = 0; it < FG_TILE_ITERS; ++it) {
-                ne[it] = false;
                 const int rc = rci[it];
-                if (rc >= 0 && (rc >> 16) < nr && (rc & 0xFFFF) < CW) {
-                    const int il = rc & 0xFFFF, j = j_gen + (rc >> 16);
-                    const ColInfo ci = colT[il];
-                    int iy = floor_i32(__fmul_rn(__int2float_rn(j), delta));
-                    iy = min(max(iy, 0), c.in_h - 1);
-                    const uint64_t th64 = __ldg(thr + (size_t)iy * c.in_w + ci.ixc);
-                    const uint64_t h = mix3_row(ci.h, j);
-                    uint64_t s0, s3;
-                    if (c.seeding == 0) { s0 = pcg_word_pair<0>(h); s3 = pcg_word_pair<3>(h); }
-                    else { Xoshiro t; seed_splitmix(t, h); s0 = t.s0; s3 = t.s3; }
-                    const uint64_t m1 = (rotl64(s0 + s3, 23) + s0) >> 11;
-                    general |= (th64 == FG_THR_GENERAL);
-                    ne[it] = (th64 != FG_THR_GENERAL) && (m1 > th64);
-                }
-            }
-            if (general) wtot[FG_TILE_WARPS] = 1;
-#pragma unroll
-            for (int it = 0; it < FG_TILE_ITERS; ++it) {
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne[it]);
+                // one bit per cell from the first-draw bitmap (k_first_draw_bitmap); the words were
+                // fetched while the previous group was in its dense phase
+                const bool ne = (rc >= 0 && (rc >> 16) < nr && (rc & 0xFFFF) < CW) && ((bmw[it] >> bsh[it]) & 1u);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne);
                 masks[it] = m;
                 if (lane == 0) cntA[it * FG_TILE_WARPS + warp] = __popc(m);
             }
+            load_bm(j_gen + nr); // prefetch for the next group (its rows start at j_gen + nr)
             __syncthreads();
-            if (wtot[FG_TILE_WARPS]) { // a cell of this group needs the general path: hand the rest of the segment over
-                if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
-                return;
-            }
             // exclusive scan of the FG_TILE_NE (it, warp) counts, redundantly in every warp (no extra
             // barrier): lane l holds entries K*l .. K*l+K-1; the offsets this thread needs come back by shuffle
             uint32_t offs[FG_TILE_ITERS];
@@ -357,8 +406,12 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                     iy = min(max(iy, 0), c.in_h - 1);
                     const double e = __ldg(ev + (size_t)iy * c.in_w + ci.ixc);
                     seed_small_rng(rng, mix3_row(ci.h, j), c.seeding);
-                    double p = standard_f64(rng); // first draw (known > e)
-                    while (p > e) { p = __dmul_rn(p, standard_f64(rng)); ++q; }
+                    if (e < 0.0) {
+                        wtot[FG_TILE_WARPS] = 1; // lambda' >= 12 / non-finite: general path only (flag read after the barrier)
+                    } else {
+                        double p = standard_f64(rng); // first draw (known > e from the bitmap)
+                        while (p > e) { p = __dmul_rn(p, standard_f64(rng)); ++q; }
+                    }
                 }
                 // block-wide exclusive scan of q
                 uint32_t incl = q;
@@ -382,7 +435,7 @@ k_pixelwise_strip(const uint64_t* __restrict__ thr_planes, const double* __restr
                     total = __shfl_sync(0xFFFFFFFFu, wincl, FG_TILE_WARPS - 1);
                     boff = __shfl_sync(0xFFFFFFFFu, wincl - v, warp);
                 }
-                if (used + total >= GC) { // uniform: grain ring overflow (== GC would alias an empty ring)
+                if (used + total >= GC || wtot[FG_TILE_WARPS]) { // uniform: grain ring overflow (== GC would alias an empty ring) or a general-path cell
                     if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
                     return;
                 }
@@ -694,12 +747,28 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
                 const float* d_offsets, float* d_out) {
     TilePlan pl = tile_plan(ctx, p, c, n_planes);
     if (!pl.ok) return 1;
-    const TileCfg& g = pl.cfg;
     const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
     const size_t n_in = in_stride * n_planes;
-    const uint32_t units = (uint32_t)g.n_strips * g.n_segs * n_planes;
+    // first-draw bitmap geometry: every cell any strip window of this band can touch (+2 cells of slack
+    // against f32-vs-f64 rounding; the kernel re-checks its windows against these bounds)
+    TileCfg g = pl.cfg;
+    {
+        const double iz = 1.0 / (double)p->zoom, dl = p->delta, rmd = p->rm;
+        const double i0 = std::floor((0.5 * iz - (double)c.off_max_x - rmd) / dl) - 2.0;
+        const double i1 = std::floor((((double)p->out_w - 0.5) * iz - (double)c.off_min_x + rmd) / dl) + 2.0;
+        const double j0 = std::floor((((double)c.row_begin + 0.5) * iz - (double)c.off_max_y - rmd) / dl) - 2.0;
+        const double j1 = std::floor((((double)c.row_end - 0.5) * iz - (double)c.off_min_y + rmd) / dl) + 2.0;
+        if (!(i0 > -2.0e9 && i1 < 2.0e9 && j0 > -2.0e9 && j1 < 2.0e9)) return 1;
+        g.bm_i0 = (int)i0; g.bm_j0 = (int)j0;
+        g.bm_cols = (int)(i1 - i0 + 1.0); g.bm_rows = (int)(j1 - j0 + 1.0);
+        g.bm_pitchw = (uint32_t)((g.bm_cols + 31) / 32);
+    }
+    const size_t bm_plane_words = (size_t)g.bm_rows * g.bm_pitchw;
+    if (bm_plane_words * (size_t)n_planes * 4 > ((size_t)12 << 30) || g.bm_pitchw * 32u / 256u + 1u > 65535u) return 1;
     int rc;
     if ((rc = ensure(ctx, ctx->thr, n_in * 16))) return rc;
+    if ((rc = ensure(ctx, ctx->bitmap, bm_plane_words * (size_t)n_planes * 4))) return rc;
+    const uint32_t units = (uint32_t)g.n_strips * g.n_segs * n_planes;
     if ((rc = ensure(ctx, ctx->tiles, (size_t)units * sizeof(TileRef) + 64))) return rc;
     uint64_t* d_thr = (uint64_t*)ctx->thr.p;
     double* d_e = (double*)((unsigned char*)ctx->thr.p + n_in * 8);
@@ -710,10 +779,17 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
     const unsigned tb = (unsigned)std::min<size_t>((n_in + 255) / 256, (size_t)ctx->sm_count * 16);
     k_thresholds<<<tb, 256, 0, s>>>(d_lambda, n_in, p->delta, d_thr, d_e);
     FG_CUDA(ctx, cudaGetLastError());
+    uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
+    {
+        dim3 bgrid((unsigned)((g.bm_rows + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
+        k_first_draw_bitmap<<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, g.bm_cols,
+                                                  g.bm_rows, g.bm_pitchw, c);
+        FG_CUDA(ctx, cudaGetLastError());
+    }
     const float2* off = (const float2*)d_offsets;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
 #define FG_LAUNCH_STRIP(SP, LG)                                                                                   \
-    k_pixelwise_strip<SP, LG><<<units, FG_TILE_THREADS, g.total, s>>>(d_thr, d_e, in_stride, off, d_out, out_stride, \
+    k_pixelwise_strip<SP, LG><<<units, FG_TILE_THREADS, g.total, s>>>(d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, \
                                                                        d_fblist, d_fbcount, units, g, c)
     if (c.rad.lognorm) {
         switch (pl.spwc) {
@@ -737,7 +813,7 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
                                                  chunks, c);
     FG_CUDA(ctx, cudaGetLastError());
     FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host, d_fbcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    ctx->stats.launches += 3;
+    ctx->stats.launches += 4;
     ctx->stats.tiles_total = units;
     ctx->fb_pending = true;
     return FG_OK;
