@@ -17,7 +17,7 @@ FG_DIST_CONST, FG_DIST_LOGNORM = 0, 1
 FG_STREAM_CELL, FG_STREAM_PIXEL = 1, 2
 FG_COLOR_LUMA, FG_COLOR_RGB = 0, 1
 FG_ALGO_GRAIN, FG_ALGO_PIXEL = 1, 2
-FG_PATH_AUTO, FG_PATH_DIRECT, FG_PATH_TILED = 0, 1, 2
+FG_PATH_AUTO, FG_PATH_DIRECT, FG_PATH_TILED, FG_PATH_STAGED = 0, 1, 2, 3
 
 
 class FgParams(C.Structure):
@@ -36,7 +36,7 @@ class FgStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("launches", C.c_uint32), ("tiles_total", C.c_uint32), ("tiles_fallback", C.c_uint32),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("strip_ms", C.c_float), ("reserved", C.c_uint32)]
+                ("strip_ms", C.c_float), ("strip_launches", C.c_uint32)]
 
 
 class FghParams(C.Structure):

@@ -8,6 +8,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <cstdlib>
 #include "fg_ctx.cuh"
 #include "fg_kernels.cuh"
 #include "fg_tile.cuh"
@@ -58,7 +59,7 @@ int validate(fg_ctx* ctx, const fg_params* p) {
         if (p->row_begin >= p->row_end || p->row_end > p->out_h)
             return set_err(ctx, FG_ERR_INVALID, "row band must satisfy row_begin < row_end <= out_h");
     }
-    if (p->path > FG_PATH_TILED) return set_err(ctx, FG_ERR_INVALID, "unknown path");
+    if (p->path > FG_PATH_STAGED) return set_err(ctx, FG_ERR_INVALID, "unknown path");
     return FG_OK;
 }
 
@@ -119,9 +120,9 @@ int pixelwise_device(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
     const int band_rows = c.row_end - c.row_begin;
     uint32_t path = p->path;
-    if (path == FG_PATH_AUTO) path = FG_PATH_TILED;
-    if (path == FG_PATH_TILED) {
-        int rc = tile_render(ctx, p, c, n_planes, d_lambda, d_offsets, d_out);
+    if (path == FG_PATH_AUTO) path = FG_PATH_STAGED;
+    if (path == FG_PATH_TILED || path == FG_PATH_STAGED) {
+        int rc = tile_render(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, path);
         if (rc != 1) return rc; // 1 = "tiled path not applicable, use direct"
     }
     dim3 grid((p->out_w + 31) / 32, (band_rows + 7) / 8, n_planes), block(32, 8);
@@ -290,6 +291,14 @@ int fg_context_create(fg_ctx** out, int device) {
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    {
+        // cell-table budget: at most half of the device memory, 48 GiB by default
+        ctx->table_max = std::min<size_t>(ctx->table_max, prop.totalGlobalMem / 2);
+        if (const char* v = std::getenv("FG_B200_TABLE_MAX_BYTES")) {
+            const unsigned long long b = std::strtoull(v, nullptr, 10);
+            if (b >= (1ULL << 20)) ctx->table_max = (size_t)b;
+        }
+    }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
@@ -308,7 +317,7 @@ void fg_context_destroy(fg_ctx* ctx) {
         ScopedDevice dev(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         for (DevBuf* b : {&ctx->lambda, &ctx->out, &ctx->offsets, &ctx->bits, &ctx->counts, &ctx->scan_out, &ctx->scan_tmp,
-                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->bitmap, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut})
+                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->bitmap, &ctx->rowinfo, &ctx->ptab, &ctx->gtab, &ctx->fbtotal, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut})
             release(*b);
         for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -324,6 +333,7 @@ void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
     *out = ctx->stats;
     if (ctx->fb_pending) { // meaningful once the stream is synchronised
         out->tiles_fallback = ctx->fb_count_host;
+        out->strip_launches = ctx->strip_launches;
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) out->strip_ms = ms;
         else cudaGetLastError();

@@ -34,10 +34,12 @@ struct fg_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     // pools
-    DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, bitmap, rgb_in, rgb_out, chroma, lut;
+    DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, bitmap, rowinfo, ptab, gtab, fbtotal, rgb_in, rgb_out, chroma, lut;
     bool tables_ready = false;
     uint32_t fb_count_host = 0; // tiled path: fallback-list length of the last render (valid after a stream sync)
     bool fb_pending = false;
+    size_t table_max = (size_t)48 << 30; // cell-table budget per band (FG_B200_TABLE_MAX_BYTES overrides; tests)
+    uint32_t strip_launches = 0; // strip-kernel launches of the last pixel-wise render (row sub-bands)
 };
 
 namespace {

@@ -96,8 +96,10 @@ __global__ void __launch_bounds__(256) k_pixelwise_direct_tiles(const float* __r
                                                                  float* __restrict__ out, size_t out_stride,
                                                                  const TileRef* __restrict__ tiles,
                                                                  const uint32_t* __restrict__ n_tiles, uint32_t tile_cap,
-                                                                 uint32_t chunks_per_tile, RenderConsts c) {
+                                                                 uint32_t chunks_per_tile, uint32_t* __restrict__ n_total,
+                                                                 RenderConsts c) {
     const uint32_t nt = min(*n_tiles, tile_cap);
+    if (n_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_total, nt); // running count over the bands of a render
     const uint64_t work = (uint64_t)nt * chunks_per_tile;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (uint64_t wi = blockIdx.x; wi < work; wi += gridDim.x) {

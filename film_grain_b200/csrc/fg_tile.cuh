@@ -27,6 +27,7 @@
 #pragma once
 #include "fg_ctx.cuh"
 #include "fg_kernels.cuh"
+#include "fg_stage.cuh"
 
 namespace fg {
 
@@ -119,7 +120,8 @@ struct TileCfg {
     int bm_i0, bm_j0;     // first cell column / row of the first-draw bitmap
     int bm_cols, bm_rows; // its extent in cells
     uint32_t bm_pitchw;   // 32-bit words per bitmap row
-    uint32_t off_col, off_P, off_G, off_R2, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, total;
+    uint32_t ppitch;      // staged mode: cell-table prefix entries per row
+    uint32_t off_col, off_P, off_G, off_R2, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, off_rows, total;
 };
 
 #ifndef FG_TILE_WARPS
@@ -180,12 +182,20 @@ __device__ __noinline__ uint32_t col_range_packed(float xg, float rm, float delt
     return (uint32_t)(2 * (i0 - i_lo)) | ((uint32_t)(2 * (i1 - i_lo + 1)) << 16);
 }
 
-template <int SPWC, bool LOGN>
+// the cell table of fg_stage.cuh (STAGED instances of the strip kernel load their windows from it)
+struct CellTable {
+    const uint32_t* Pg;
+    const uint64_t* rowbase;
+    const float2* Gg;
+    const float* R2g;
+};
+
+template <int SPWC, bool LOGN, bool STAGED>
 __global__ void __launch_bounds__(FG_TILE_THREADS, 1)
 k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words, const double* __restrict__ e_planes, size_t in_stride,
                   const float2* __restrict__ offsets_input, float* __restrict__ out, size_t out_stride,
                   TileRef* __restrict__ fb_list, uint32_t* __restrict__ fb_count, uint32_t fb_cap, TileCfg cfg,
-                  RenderConsts c) {
+                  RenderConsts c, CellTable tab) {
     extern __shared__ __align__(16) unsigned char smem[];
     ColInfo* colT = (ColInfo*)(smem + cfg.off_col);
     uint16_t* P = (uint16_t*)(smem + cfg.off_P);
@@ -197,6 +207,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
     uint32_t* wtot = (uint32_t*)(smem + cfg.off_wtot); // [NW] warp totals, [NW] general-path flag
     uint32_t* pcount = (uint32_t*)(smem + cfg.off_pcount);
     float2* wpair = (float2*)(smem + cfg.off_wpair);
+    uint32_t* rowA = (uint32_t*)(smem + cfg.off_rows); // STAGED: [RH] first table prefix of the window, [RH] count, [RH] ring position
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -230,6 +241,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
     const int CW = (int)CWl, CW1 = CW + 1;
     const int PS = cfg.PS, RH = cfg.RH;
 
+    if (!STAGED)
     for (int il = tid; il < CW; il += FG_TILE_THREADS) {
         ColInfo ci;
         int i = i_lo + il;
@@ -328,8 +340,77 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             used = head - tail + (head < tail ? GC : 0u);
         }
 
+        // =================== STAGED: load cell rows j_gen .. j_hi from the cell table ===================
+        if (STAGED && j_gen <= j_hi) {
+            const int nn = j_hi - j_gen + 1; // <= RH
+            uint32_t* rowN = rowA + RH;
+            uint32_t* rowH = rowN + RH;
+            const size_t trow0 = (size_t)plane * cfg.bm_rows + (size_t)(j_gen - cfg.bm_j0);
+            const uint32_t tcol0 = (uint32_t)(i_lo - cfg.bm_i0);
+            for (int t = tid; t < nn; t += FG_TILE_THREADS) {
+                const uint32_t* pr = tab.Pg + (trow0 + t) * cfg.ppitch + tcol0;
+                const uint32_t a = __ldg(pr), b = __ldg(pr + CW);
+                rowA[t] = a;
+                rowN[t] = b - a;
+            }
+            __syncthreads();
+            if (warp == 0) { // ring position of every row's first grain
+                uint32_t carry = head;
+                for (int t0 = 0; t0 < nn; t0 += 32) {
+                    const uint32_t v = (t0 + lane < nn) ? rowN[t0 + lane] : 0u;
+                    uint32_t incl = v;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                        if (lane >= d) incl += u;
+                    }
+                    if (t0 + lane < nn) rowH[t0 + lane] = carry + incl - v; // not yet reduced mod GC
+                    carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                }
+                if (lane == 0) wtot[0] = carry - head;
+            }
+            __syncthreads();
+            const uint32_t total = wtot[0];
+            if (used + total >= GC) { // uniform: grain ring overflow (== GC would alias an empty ring)
+                if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
+                return;
+            }
+            for (int t = warp; t < nn; t += FG_TILE_WARPS) {
+                const uint32_t a = rowA[t], n = rowN[t];
+                uint32_t h = rowH[t]; // < 2 * GC
+                if (h >= GC) h -= GC;
+                int rr = rr_gen + t;
+                if (rr >= RH) rr -= RH;
+                const uint32_t* pr = tab.Pg + (trow0 + t) * cfg.ppitch + tcol0;
+                uint16_t* prow = P + rr * PS;
+                for (int ci = lane; ci < CW1; ci += 32) {
+                    uint32_t v = __ldg(pr + ci) - a + h;
+                    if (v >= GC) v -= GC;
+                    prow[ci] = (uint16_t)v;
+                }
+                const size_t gsrc = (size_t)__ldg(tab.rowbase + trow0 + t) + a;
+                for (uint32_t k = lane; k < n; k += 32) {
+                    uint32_t pos = h + k;
+                    if (pos >= GC) pos -= GC;
+                    const float2 gr = __ldg(tab.Gg + gsrc + k);
+                    G[pos] = gr;
+                    if (pos < FG_TILE_GPAD) G[GC + pos] = gr; // mirror: unrolled reads never wrap
+                    if (LOGN) {
+                        const float rr2 = __ldg(tab.R2g + gsrc + k);
+                        R2[pos] = rr2;
+                        if (pos < FG_TILE_GPAD) R2[GC + pos] = rr2;
+                    }
+                }
+            }
+            head += total;
+            if (head >= GC) head -= GC;
+            used += total;
+            j_gen += nn;
+            rr_gen += nn;
+            if (rr_gen >= RH) rr_gen -= RH;
+        }
         // =================== generation: cell rows j_gen .. j_hi in groups of <= R rows ===================
-        while (j_gen <= j_hi) {
+        while (!STAGED && j_gen <= j_hi) {
             const int nr = min(r_cur, j_hi - j_gen + 1);
             if (j_bm != j_gen) load_bm(j_gen); // first group, or the window jumped (uniform)
             // ---- phase A: first-draw filter on every cell of the group (4 independent hash chains
@@ -646,7 +727,7 @@ struct TilePlan { TileCfg cfg; int spwc; bool ok; };
 inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 // Choose the strip geometry for a render; ok == false -> the tiled path does not apply.
-TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes) {
+TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, bool staged) {
     TilePlan pl{};
     pl.ok = false;
     if (p->n_samples > (1u << 20)) return pl;
@@ -677,11 +758,12 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
             TileCfg g{};
             g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R;
             uint32_t off = 0;
-            g.off_col = off; off = align_up(off + (uint32_t)CWB * 16u, 16);
+            g.off_col = off; off = align_up(off + (staged ? 0u : (uint32_t)CWB * 16u), 16);
             g.off_P = off; off = align_up(off + (uint32_t)RH * PS * 2u, 16);
-            g.off_list = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
-            g.off_E = off; off = align_up(off + (uint32_t)(R * (CWB + 1) + 2) * 2u, 16);
-            g.off_cnt = off; off = align_up(off + (uint32_t)(FG_TILE_NE + 8) * 4u, 16);
+            g.off_list = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
+            g.off_E = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
+            g.off_cnt = off; off = align_up(off + (staged ? 0u : (uint32_t)(FG_TILE_NE + 8) * 4u), 16);
+            g.off_rows = off; off = align_up(off + (staged ? (uint32_t)RH * 12u : 0u), 16);
             g.off_wtot = off; off = align_up(off + (uint32_t)(FG_TILE_WARPS + 4) * 4u, 16);
             g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
             g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
@@ -705,7 +787,7 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     g.n_strips = (int)((p->out_w + 31) / 32);
     // segment height: maximise (wave efficiency over the SMs) x (1 - start-up share).  A segment
     // regenerates the cell rows of its first window (RH rows = RH*delta*zoom pixel rows of work).
-    const double startup_rows = (double)g.RH * delta * (double)p->zoom;
+    const double startup_rows = (double)g.RH * delta * (double)p->zoom * (staged ? 0.05 : 1.0); // staged: a load, not a generation
     const long long per_seg_units = (long long)g.n_strips * n_planes;
     int best_n = 1;
     double best_eff = -1.0;
@@ -729,28 +811,49 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     return pl;
 }
 
+template <int SP, bool LG, bool ST>
+cudaError_t strip_attr(int smem) {
+    return cudaFuncSetAttribute(k_pixelwise_strip<SP, LG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
 int tile_setup(fg_ctx* ctx) {
     cudaError_t e;
     const int smem = (int)ctx->smem_optin;
-    if ((e = cudaFuncSetAttribute(k_pixelwise_strip<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<FG_TILE_SPW_MAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_strip<FG_TILE_SPW_MAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+#define FG_ATTR(SP)                                                                                               \
+    if ((e = strip_attr<SP, false, false>(smem)) != cudaSuccess || (e = strip_attr<SP, true, false>(smem)) != cudaSuccess || \
+        (e = strip_attr<SP, false, true>(smem)) != cudaSuccess || (e = strip_attr<SP, true, true>(smem)) != cudaSuccess)     \
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_strip)");
+    FG_ATTR(4)
+    FG_ATTR(8)
+    FG_ATTR(FG_TILE_SPW_MAX)
+#undef FG_ATTR
     return FG_OK;
 }
 
-// returns FG_OK (rendered), 1 (not applicable: caller uses the direct kernel) or an error
-int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
-                const float* d_offsets, float* d_out) {
-    TilePlan pl = tile_plan(ctx, p, c, n_planes);
+template <bool LG, bool ST, typename... Args>
+void launch_strip(int spwc, uint32_t units, uint32_t smem, cudaStream_t s, Args... args) {
+    switch (spwc) {
+    case 4: k_pixelwise_strip<4, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
+    case 8: k_pixelwise_strip<8, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
+    default: k_pixelwise_strip<FG_TILE_SPW_MAX, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
+    }
+}
+
+// Upper bound on the cell table (prefixes + grains) of one band; larger renders are split into row bands.
+#ifndef FG_TABLE_BYTES_MAX
+#define FG_TABLE_BYTES_MAX ((size_t)48 << 30)
+#endif
+
+// One band [c.row_begin, c.row_end).  returns FG_OK (rendered), 1 (tiled path not applicable), 2 (staged
+// mode not possible for this band: caller retries with in-kernel generation) or an error.
+int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
+                     const float* d_offsets, float* d_out, bool staged, uint32_t* d_fbtotal) {
+    TilePlan pl = tile_plan(ctx, p, c, n_planes, staged);
     if (!pl.ok) return 1;
     const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
     const size_t n_in = in_stride * n_planes;
-    // first-draw bitmap geometry: every cell any strip window of this band can touch (+2 cells of slack
-    // against f32-vs-f64 rounding; the kernel re-checks its windows against these bounds)
+    // cell rectangle of the band: every cell any strip window can touch (+2 cells of slack against
+    // f32-vs-f64 rounding; the kernel re-checks its windows against these bounds)
     TileCfg g = pl.cfg;
     {
         const double iz = 1.0 / (double)p->zoom, dl = p->delta, rmd = p->rm;
@@ -762,9 +865,13 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
         g.bm_i0 = (int)i0; g.bm_j0 = (int)j0;
         g.bm_cols = (int)(i1 - i0 + 1.0); g.bm_rows = (int)(j1 - j0 + 1.0);
         g.bm_pitchw = (uint32_t)((g.bm_cols + 31) / 32);
+        g.ppitch = (uint32_t)((g.bm_cols + 1 + 7) / 8 * 8);
     }
     const size_t bm_plane_words = (size_t)g.bm_rows * g.bm_pitchw;
     if (bm_plane_words * (size_t)n_planes * 4 > ((size_t)12 << 30) || g.bm_pitchw * 32u / 256u + 1u > 65535u) return 1;
+    const size_t n_rows_all = (size_t)g.bm_rows * n_planes;
+    const size_t pg_bytes = n_rows_all * g.ppitch * 4;
+    if (staged && (pg_bytes > ctx->table_max / 2 || g.bm_rows > 2000000)) return 2;
     int rc;
     if ((rc = ensure(ctx, ctx->thr, n_in * 16))) return rc;
     if ((rc = ensure(ctx, ctx->bitmap, bm_plane_words * (size_t)n_planes * 4))) return rc;
@@ -786,35 +893,118 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
                                                   g.bm_rows, g.bm_pitchw, c);
         FG_CUDA(ctx, cudaGetLastError());
     }
+    ctx->stats.launches += 2;
+    CellTable tab{};
+    if (staged) {
+        // row capacities from the expected grain counts, then the table itself
+        const size_t s_bytes = align_up((uint32_t)((size_t)n_planes * p->in_h * 8), 256);
+        const size_t base_bytes = (n_rows_all + 1) * 8, cap_bytes = n_rows_all * 4;
+        if ((rc = ensure(ctx, ctx->rowinfo, s_bytes + base_bytes + cap_bytes + 256 + 64))) return rc;
+        if ((rc = ensure(ctx, ctx->ptab, pg_bytes))) return rc;
+        double* d_S = (double*)ctx->rowinfo.p;
+        uint64_t* d_rowbase = (uint64_t*)((unsigned char*)ctx->rowinfo.p + s_bytes);
+        uint32_t* d_rowcap = (uint32_t*)((unsigned char*)d_rowbase + (base_bytes + 255) / 256 * 256);
+        uint32_t* d_overflow = (uint32_t*)((unsigned char*)d_rowcap + (cap_bytes + 63) / 64 * 64);
+        k_row_expect<<<dim3(p->in_h, n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, d_S, c);
+        FG_CUDA(ctx, cudaGetLastError());
+        k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, d_rowbase, d_rowcap, c);
+        FG_CUDA(ctx, cudaGetLastError());
+        FG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 4, s));
+        uint64_t total = 0;
+        FG_CUDA(ctx, cudaMemcpyAsync(&total, d_rowbase + n_rows_all, 8, cudaMemcpyDeviceToHost, s));
+        FG_CUDA(ctx, cudaStreamSynchronize(s));
+        const size_t bpg = c.rad.lognorm ? 12 : 8;
+        if (total == 0xFFFFFFFFFFFFFFFFULL || total * bpg + pg_bytes > ctx->table_max) return 2;
+        const size_t g_bytes = ((size_t)total * 8 + 255) / 256 * 256;
+        if ((rc = ensure(ctx, ctx->gtab, g_bytes + (c.rad.lognorm ? (size_t)total * 4 : 0) + 256))) {
+            if (rc == FG_ERR_OOM) { ctx->err.clear(); return 2; }
+            return rc;
+        }
+        float2* d_G = (float2*)ctx->gtab.p;
+        float* d_R2 = (float*)((unsigned char*)ctx->gtab.p + g_bytes);
+        StageGeo geo{g.bm_i0, g.bm_j0, g.bm_cols, g.bm_rows, g.bm_pitchw, g.ppitch};
+        const dim3 ggrid((unsigned)g.bm_rows, (unsigned)n_planes);
+        if (c.rad.lognorm)
+            k_gen_rows<true><<<ggrid, FG_GEN_THREADS, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
+                                                               d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, c);
+        else
+            k_gen_rows<false><<<ggrid, FG_GEN_THREADS, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
+                                                                d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, c);
+        FG_CUDA(ctx, cudaGetLastError());
+        uint32_t overflow = 0;
+        FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));
+        FG_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->stats.launches += 3;
+        if (overflow) return 2; // a row outgrew its expected size + 8 sigma: regenerate in-kernel instead
+        tab.Pg = (const uint32_t*)ctx->ptab.p;
+        tab.rowbase = d_rowbase;
+        tab.Gg = d_G;
+        tab.R2g = d_R2;
+    }
     const float2* off = (const float2*)d_offsets;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-#define FG_LAUNCH_STRIP(SP, LG)                                                                                   \
-    k_pixelwise_strip<SP, LG><<<units, FG_TILE_THREADS, g.total, s>>>(d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, \
-                                                                       d_fblist, d_fbcount, units, g, c)
-    if (c.rad.lognorm) {
-        switch (pl.spwc) {
-        case 4: FG_LAUNCH_STRIP(4, true); break;
-        case 8: FG_LAUNCH_STRIP(8, true); break;
-        default: FG_LAUNCH_STRIP(FG_TILE_SPW_MAX, true); break;
-        }
+    if (staged) {
+        if (c.rad.lognorm) launch_strip<true, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
+        else launch_strip<false, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
     } else {
-        switch (pl.spwc) {
-        case 4: FG_LAUNCH_STRIP(4, false); break;
-        case 8: FG_LAUNCH_STRIP(8, false); break;
-        default: FG_LAUNCH_STRIP(FG_TILE_SPW_MAX, false); break;
-        }
+        if (c.rad.lognorm) launch_strip<true, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
+        else launch_strip<false, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
     }
-#undef FG_LAUNCH_STRIP
     FG_CUDA(ctx, cudaGetLastError());
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
     const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);
     const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units * chunks, (uint64_t)ctx->sm_count * 8);
     k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
-                                                 chunks, c);
+                                                 chunks, d_fbtotal, c);
     FG_CUDA(ctx, cudaGetLastError());
-    FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host, d_fbcount, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    ctx->stats.launches += 4;
-    ctx->stats.tiles_total = units;
+    ctx->stats.launches += 2;
+    ctx->stats.tiles_total += units;
+    ctx->strip_launches += 1;
+    return FG_OK;
+}
+
+// returns FG_OK (rendered), 1 (not applicable: caller uses the direct kernel) or an error.
+// path: FG_PATH_AUTO / FG_PATH_STAGED try the cell table first and fall back to in-kernel generation
+// (FG_PATH_TILED) when the table does not fit or a row overflowed.
+int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
+                const float* d_offsets, float* d_out, uint32_t path) {
+    int rc;
+    if ((rc = ensure(ctx, ctx->fbtotal, 64))) return rc;
+    uint32_t* d_fbtotal = (uint32_t*)ctx->fbtotal.p;
+    FG_CUDA(ctx, cudaMemsetAsync(d_fbtotal, 0, 4, ctx->stream));
+    ctx->strip_launches = 0;
+    bool staged = path != FG_PATH_TILED;
+    rc = tile_render_band(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, staged, d_fbtotal);
+    if (rc == 2) {
+        // the whole band does not fit one table: split it into row sub-bands, else generate in-kernel
+        const int band = c.row_end - c.row_begin;
+        int done = c.row_begin;
+        bool ok = true;
+        for (int parts = 2; parts <= 64 && done == c.row_begin; parts *= 2) {
+            const int rows = (band + parts - 1) / parts;
+            if (rows < 64) break;
+            ok = true;
+            for (int y = c.row_begin; y < c.row_end && ok; y += rows) {
+                RenderConsts cb = c;
+                cb.row_begin = y;
+                cb.row_end = std::min(y + rows, c.row_end);
+                rc = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, true, d_fbtotal);
+                if (rc == 2 || rc == 1) { ok = false; break; }
+                if (rc) return rc;
+                done = cb.row_end;
+            }
+            if (ok) break;
+        }
+        if (done < c.row_end) { // finish (or redo) the rest with in-kernel generation
+            RenderConsts cb = c;
+            cb.row_begin = done;
+            rc = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, false, d_fbtotal);
+            if (rc) return rc;
+        }
+        rc = FG_OK;
+    }
+    if (rc) return rc;
+    FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host, d_fbtotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->fb_pending = true;
     return FG_OK;
 }

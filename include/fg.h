@@ -52,7 +52,12 @@ enum { FG_ALGO_GRAIN = 1, FG_ALGO_PIXEL = 2 };            /* Algo (resolved), sr
 enum { FG_SEEDING_RAND_0_8 = 0, FG_SEEDING_RAND_0_9 = 1 };
 
 /* Which kernel family serves fg_render_pixelwise (diagnostics / tests; AUTO in production). */
-enum { FG_PATH_AUTO = 0, FG_PATH_DIRECT = 1, FG_PATH_TILED = 2 };
+enum {
+    FG_PATH_AUTO = 0,   /* staged, falling back to tiled, falling back to direct */
+    FG_PATH_DIRECT = 1, /* per-sample regeneration (the reference's own structure) */
+    FG_PATH_TILED = 2,  /* strip kernel generating its cell windows in shared memory */
+    FG_PATH_STAGED = 3  /* cell table generated once per band in HBM, strip kernel loads windows */
+};
 
 /* Parameter block of one plane render = Params (src/params.rs:45-68) + Derived
  * (src/model.rs:167-179) reduced to what the integrators read; the Rust side fills it
@@ -92,8 +97,8 @@ typedef struct fg_stats {
     uint32_t tiles_total;     /* pixel-wise tiled path: tiles rendered */
     uint32_t tiles_fallback;  /*   of which re-rendered by the direct kernel (capacity / lambda>=12) */
     uint64_t h2d_bytes, d2h_bytes;
-    float strip_ms;           /* pixel-wise tiled path: device time of the strip kernel alone */
-    uint32_t reserved;
+    float strip_ms;           /* pixel-wise tiled path: device time of the (last) strip-kernel launch */
+    uint32_t strip_launches;  /*   strip-kernel launches of the call (row sub-bands; normally 1) */
 } fg_stats;
 
 int fg_abi_version(void);

@@ -101,7 +101,7 @@ PIXEL_CASES = [
 ]
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["direct", "tiled"])
+@pytest.mark.parametrize("path", [1, 2, 3], ids=["direct", "tiled", "staged"])
 @pytest.mark.parametrize("name,w,h,kw", PIXEL_CASES, ids=[c[0] for c in PIXEL_CASES])
 def test_pixelwise_matches_oracle(ctx, name, w, h, kw, path):
     p = O.make_params(algo=O.ALGO_PIXEL, **kw)
@@ -115,22 +115,24 @@ def test_pixelwise_matches_oracle(ctx, name, w, h, kw, path):
     assert 0.0 < ref.mean() < 1.0
 
 
-def test_tiled_path_is_taken_and_fallback_is_exact(ctx):
+@pytest.mark.parametrize("path", [2, 3], ids=["tiled", "staged"])
+def test_tiled_path_is_taken_and_fallback_is_exact(ctx, path):
     """The strip kernel serves ordinary content itself; saturated content (u8 255 -> 4.4 grains per
-    cell) overflows its grain ring and must come back bit-identical through the fallback list."""
+    cell) overflows its grain ring and must come back bit-identical through the fallback list.
+    path 2 generates the cell windows inside the strip kernel, path 3 loads them from the cell table."""
     w, h = 160, 140
     p = O.make_params(radius=0.1, n_samples=16, algo=O.ALGO_PIXEL)
     d, off, off_in = O.derive_common(p, w, h)
     img = noise_u8(w, h, seed=3)
     lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
-    got = ctx.render_pixelwise(fg_params_from(p, d, path=2), lam, off_in)
+    got = ctx.render_pixelwise(fg_params_from(p, d, path=path), lam, off_in)
     st = ctx.stats()
     assert st.tiles_total > 0 and st.tiles_fallback == 0, (st.tiles_total, st.tiles_fallback)
     assert np.array_equal(got, O.render_pixelwise(lam, p, d, off_in))
     img2 = img.copy()
     img2[40:, 50:, :] = 255  # saturated block
     lam2 = lambda_from_u8(img2[:, :, 0], d.inv_e_pi_r2)
-    got2 = ctx.render_pixelwise(fg_params_from(p, d, path=2), lam2, off_in)
+    got2 = ctx.render_pixelwise(fg_params_from(p, d, path=path), lam2, off_in)
     st2 = ctx.stats()
     assert 0 < st2.tiles_fallback <= st2.tiles_total, (st2.tiles_total, st2.tiles_fallback)
     assert np.array_equal(got2, O.render_pixelwise(lam2, p, d, off_in))
@@ -138,8 +140,26 @@ def test_tiled_path_is_taken_and_fallback_is_exact(ctx):
     p3 = O.make_params(radius=0.1, n_samples=4, algo=O.ALGO_PIXEL, cell_delta=0.7)
     d3, _, off_in3 = O.derive_common(p3, w, h)
     lam3 = lambda_from_u8(img2[:, :, 0], d3.inv_e_pi_r2)
-    got3 = ctx.render_pixelwise(fg_params_from(p3, d3, path=2), lam3, off_in3)
+    got3 = ctx.render_pixelwise(fg_params_from(p3, d3, path=path), lam3, off_in3)
     assert np.array_equal(got3, O.render_pixelwise(lam3, p3, d3, off_in3))
+
+
+def test_staged_path_splits_into_row_bands_when_the_table_budget_is_small(monkeypatch):
+    """A render whose cell table exceeds the budget is split into row sub-bands (each with its own
+    table); the result and the fallback accounting do not change."""
+    w, h = 256, 320
+    p = O.make_params(radius=0.1, n_samples=8, algo=O.ALGO_PIXEL)
+    d, off, off_in = O.derive_common(p, w, h)
+    lam = lambda_from_u8(noise_u8(w, h, seed=9)[:, :, 0], d.inv_e_pi_r2)
+    ref = O.render_pixelwise(lam, p, d, off_in)
+    import film_grain_b200 as fg
+    monkeypatch.setenv("FG_B200_TABLE_MAX_BYTES", str(24 << 20))  # whole image needs ~55 MiB
+    with fg.Context(0) as small:
+        got = small.render_pixelwise(fg_params_from(p, d, path=3), lam, off_in)
+        st = small.stats()
+    assert st.strip_launches >= 2, st.strip_launches
+    assert st.tiles_fallback == 0
+    assert np.array_equal(ref, got)
 
 
 GRAIN_CASES = [
@@ -289,9 +309,11 @@ def test_full_size_config2_plane_properties(ctx):
     d, off, off_in = O.derive_common(p, w, h)
     img = noise_u8(w, h)  # the bench input
     lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
-    full = ctx.render_pixelwise(fg_params_from(p, d, path=2), lam, off_in)
+    full = ctx.render_pixelwise(fg_params_from(p, d, path=3), lam, off_in)
     st = ctx.stats()
     assert st.tiles_total > 0 and st.tiles_fallback == 0
+    tiled = ctx.render_pixelwise(fg_params_from(p, d, path=2), lam, off_in)
+    assert np.array_equal(tiled, full)  # in-kernel generation == cell table, every pixel
     for a, b in ((0, 6), (1237, 1243)):
         ref = O.render_pixelwise(lam, p, d, off_in, a, b)
         assert np.array_equal(ref[a:b], full[a:b])
@@ -317,9 +339,12 @@ def test_full_size_config4_band(ctx):
     a, b = 4000, 4096
     tiled = np.zeros((8192, 8192), np.float32)
     direct = np.zeros((8192, 8192), np.float32)
+    staged = np.zeros((8192, 8192), np.float32)
     ctx.render_pixelwise(fg_params_from(p, d, path=2, rows=(a, b)), lam, off_in, out=tiled)
+    ctx.render_pixelwise(fg_params_from(p, d, path=3, rows=(a, b)), lam, off_in, out=staged)
     ctx.render_pixelwise(fg_params_from(p, d, path=1, rows=(a, b)), lam, off_in, out=direct)
     assert np.array_equal(tiled[a:b], direct[a:b])
+    assert np.array_equal(staged[a:b], direct[a:b])
     ref = O.render_pixelwise(lam, p, d, off_in, a, a + 4)
     assert np.array_equal(ref[a:a + 4], tiled[a:a + 4])
 
