@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libfg_b200.so")
+SO_PATH = os.environ.get("FG_B200_LIB") or os.path.join(HERE, "libfg_b200.so")  # override: kernel experiments
 
 FG_OK, FG_ERR_INVALID, FG_ERR_OOM, FG_ERR_CUDA_STICKY = 0, -1, -2, -3
 FG_ERR_NO_DEVICE, FG_ERR_CANCELLED, FG_ERR_CUDA = -4, -5, -6

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfg_b200.so")
 SOURCES = ["fg_api.cu", os.path.join("..", "host", "film_grain.cpp")]
-DEPS = ["fg_api.cu", "fg_ctx.cuh", "fg_kernels.cuh", "fg_rng.cuh", "fg_tile.cuh", "fg_color.cuh",
+DEPS = ["fg_api.cu", "fg_ctx.cuh", "fg_kernels.cuh", "fg_rng.cuh", "fg_tile.cuh", "fg_stage.cuh", "fg_color.cuh",
         "fg_zig_tables.h", "fg_logf.h", os.path.join("..", "..", "include", "fg.h"), os.path.join("..", "..", "include", "fg_host.h"),
         os.path.join("..", "host", "film_grain.cpp"), os.path.join("..", "host", "film_grain.hpp")]
 
@@ -37,6 +37,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
            "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-ccbin", "/usr/bin/g++",
            "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += os.environ.get("FG_NVCC_EXTRA", "").split()  # experiments only (e.g. -DFG_TILE_WARPS=32)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -125,7 +125,7 @@ struct TileCfg {
 };
 
 #ifndef FG_TILE_WARPS
-#define FG_TILE_WARPS 16
+#define FG_TILE_WARPS 32
 #endif
 #define FG_TILE_THREADS (FG_TILE_WARPS * 32)
 #define FG_TILE_ITERS 4 // phase-A cells per thread per group: R*(CW+1) <= FG_TILE_CELLS
@@ -135,10 +135,15 @@ struct TileCfg {
 #define FG_TILE_SPW_MAX 8  // 32 warps x 8 = 256
 #elif FG_TILE_WARPS == 16
 #define FG_TILE_SPW_MAX 16 // samples per warp per chunk (even): N <= 256 in one chunk
+#elif FG_TILE_WARPS == 24
+#define FG_TILE_SPW_MAX 12 // 24 warps x 12 = 288
 #else
 #define FG_TILE_SPW_MAX 14 // 20 warps x 14 = 280 >= 256
 #endif
-#define FG_TILE_GPAD 4  // grain ring entries mirrored past the end (unrolled reads never wrap)
+#define FG_TILE_GPAD 8  // grain ring entries mirrored past the end (unrolled reads never wrap)
+#ifndef FG_TILE_U3
+#define FG_TILE_U3 5    // unrolled grain tests of the merged three-cell-row path
+#endif
 #define FG_TILE_USLOTS 3 // unrolled, predicated grain tests per cell-row range
 
 __device__ __forceinline__ void push_fallback(TileRef* list, uint32_t* count, uint32_t cap, int x0, int y0, int w,
@@ -159,8 +164,8 @@ __device__ __forceinline__ int cell_hi(float v, float rm, float delta) { return 
 // window arithmetic.  volatile: never cached across the CTA barriers that separate generation
 // from evaluation.
 __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    uint32_t v; // 32-bit destination: the load zero-extends, no separate conversion
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -650,6 +655,66 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                         uint32_t offA = Ps + (jpA & 0xFFFFFFu), offB = Ps + (jpB & 0xFFFFFFu);
                         const float xgA = xg_r[s], ygA = pdA.x, xgB = xg_r[s + 1], ygB = pdB.x;
                         float dminA = __int_as_float(0x7f800000), dminB = __int_as_float(0x7f800000);
+                        if ((jpA >> 24) == 3u && (jpB >> 24) == 3u) { // warp-uniform: the common case rm == delta
+                            // Three cell rows per sample: their three candidate ranges are walked as ONE
+                            // list of n = n0 + n1 + n2 grains (slot u -> row by two compares), FG_TILE_U3
+                            // predicated slots folded into a running minimum, then an early-exit remainder.
+                            uint32_t o1A = offA + PS2, o1B = offB + PS2;
+                            if (o1A >= Ps + RHPS2) o1A -= RHPS2;
+                            if (o1B >= Ps + RHPS2) o1B -= RHPS2;
+                            uint32_t o2A = o1A + PS2, o2B = o1B + PS2;
+                            if (o2A >= Ps + RHPS2) o2A -= RHPS2;
+                            if (o2B >= Ps + RHPS2) o2B -= RHPS2;
+                            const uint32_t s0A = lds_u16(offA + a2A), e0A = lds_u16(offA + b2A);
+                            const uint32_t s0B = lds_u16(offB + a2B), e0B = lds_u16(offB + b2B);
+                            const uint32_t s1A = lds_u16(o1A + a2A), e1A = lds_u16(o1A + b2A);
+                            const uint32_t s1B = lds_u16(o1B + a2B), e1B = lds_u16(o1B + b2B);
+                            const uint32_t s2A = lds_u16(o2A + a2A), e2A = lds_u16(o2A + b2A);
+                            const uint32_t s2B = lds_u16(o2B + a2B), e2B = lds_u16(o2B + b2B);
+                            const uint32_t c1A = e0A - s0A + (e0A < s0A ? GC : 0u), c1B = e0B - s0B + (e0B < s0B ? GC : 0u);
+                            const uint32_t c2A = c1A + e1A - s1A + (e1A < s1A ? GC : 0u), c2B = c1B + e1B - s1B + (e1B < s1B ? GC : 0u);
+                            const uint32_t nA = c2A + e2A - s2A + (e2A < s2A ? GC : 0u), nB = c2B + e2B - s2B + (e2B < s2B ? GC : 0u);
+                            const uint32_t t1A = s1A - c1A, t2A = s2A - c2A, t1B = s1B - c1B, t2B = s2B - c2B; // mod 2^32
+                            float2 gA[FG_TILE_U3], gB[FG_TILE_U3];
+#pragma unroll
+                            for (int u = 0; u < FG_TILE_U3; ++u) { // past n: stale but in-bounds (mirror pad)
+                                const uint32_t iA = ((uint32_t)u < c1A ? s0A : ((uint32_t)u < c2A ? t1A : t2A)) + (uint32_t)u;
+                                const uint32_t iB = ((uint32_t)u < c1B ? s0B : ((uint32_t)u < c2B ? t1B : t2B)) + (uint32_t)u;
+                                gA[u] = lds_f32x2(Gs + iA * 8u);
+                                gB[u] = lds_f32x2(Gs + iB * 8u);
+                            }
+#pragma unroll
+                            for (int u = 0; u < FG_TILE_U3; ++u) {
+                                const float gxA = ((uint32_t)u < nA) ? gA[u].x : __int_as_float(0x7f800000);
+                                const float gxB = ((uint32_t)u < nB) ? gB[u].x : __int_as_float(0x7f800000);
+                                const float dxA = __fsub_rn(xgA, gxA), dyA = __fsub_rn(ygA, gA[u].y);
+                                const float dxB = __fsub_rn(xgB, gxB), dyB = __fsub_rn(ygB, gB[u].y);
+                                dminA = fminf(dminA, __fadd_rn(__fmul_rn(dxA, dxA), __fmul_rn(dyA, dyA)));
+                                dminB = fminf(dminB, __fadd_rn(__fmul_rn(dxB, dxB), __fmul_rn(dyB, dyB)));
+                            }
+                            if (nA > FG_TILE_U3 && !(dminA <= r2)) { // remainder: exits on the first hit
+                                uint32_t u = FG_TILE_U3;
+                                do {
+                                    uint32_t gi = (u < c1A ? s0A : (u < c2A ? t1A : t2A)) + u;
+                                    if (gi >= GC) gi -= GC;
+                                    const float2 gr = lds_f32x2(Gs + gi * 8u);
+                                    const float dx = __fsub_rn(xgA, gr.x), dy = __fsub_rn(ygA, gr.y);
+                                    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    if (d2 <= r2) { dminA = d2; break; }
+                                } while (++u < nA);
+                            }
+                            if (nB > FG_TILE_U3 && !(dminB <= r2)) {
+                                uint32_t u = FG_TILE_U3;
+                                do {
+                                    uint32_t gi = (u < c1B ? s0B : (u < c2B ? t1B : t2B)) + u;
+                                    if (gi >= GC) gi -= GC;
+                                    const float2 gr = lds_f32x2(Gs + gi * 8u);
+                                    const float dx = __fsub_rn(xgB, gr.x), dy = __fsub_rn(ygB, gr.y);
+                                    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    if (d2 <= r2) { dminB = d2; break; }
+                                } while (++u < nB);
+                            }
+                        } else {
                         const uint32_t nmax = max(nrowA, nrowB);
 #pragma unroll 1
                         for (uint32_t r = 0; r < nmax; ++r) {
@@ -699,6 +764,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                             if (offA >= Ps + RHPS2) offA = Ps;
                             offB += PS2;
                             if (offB >= Ps + RHPS2) offB = Ps;
+                        }
                         }
                         cnt += ((dminA <= r2) ? 1u : 0u) + ((dminB <= r2) ? 1u : 0u);
                     }
