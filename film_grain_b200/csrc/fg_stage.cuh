@@ -18,8 +18,6 @@
 
 namespace fg {
 
-#define FG_GEN_THREADS 256
-#define FG_GEN_TILE 2048 // cells per generation tile = 64 first-draw bitmap words
 
 // Expected grains of one cell row, per (plane, input row): sum over the band's cell columns of
 // lambda' = lambda * delta^2 (src/pixelwise.rs:76-81) at the clamped input pixel of the column.
@@ -101,34 +99,50 @@ struct StageGeo {
     uint32_t ppitch;          // Pg entries per row (>= cols + 1, multiple of 8)
 };
 
-// One CTA per (cell row, plane).  The row is walked in tiles of FG_GEN_TILE cells: the tile's non-empty
-// cells (first-draw bitmap) are compacted into a list, processed one thread per cell at full occupancy
-// (seeding, Knuth continuation or the general Poisson sampler, positions, radii), and written in cell
-// order; a final scan over the tile's counts writes the prefix entries of ALL its cells.
+// One WARP per (cell row, plane), no CTA-wide barriers.  The row is walked in tiles of FG_GW_TILE cells:
+// the tile's non-empty cells (first-draw bitmap) are compacted into a list and processed 32 at a time,
+// one lane per cell at full occupancy: seeding, second Knuth draw (76% of the non-empty cells at
+// lambda' = 1/pi stop there with one grain, whose position is drawn and stored at once), Knuth
+// continuation or the general Poisson sampler for the rest.  Cells with two or more grains are the
+// divergent tail: their generator state and destination are parked in a per-warp queue and their
+// positions are drawn 32 cells at a time when the queue fills.  A final scan over the tile's counts
+// writes the prefix entries of ALL its cells.
+#define FG_GW_WARPS 4
+#define FG_GW_TILE 1024
+#define FG_GW_QCAP 64
+struct GenWarpSmem {
+    uint16_t list[FG_GW_TILE];
+    __align__(16) uint16_t cnt[FG_GW_TILE];
+    uint64_t q_s0[FG_GW_QCAP], q_s1[FG_GW_QCAP], q_s2[FG_GW_QCAP], q_s3[FG_GW_QCAP], q_dst[FG_GW_QCAP];
+    uint32_t q_q[FG_GW_QCAP];
+    float q_sx[FG_GW_QCAP];
+};
+
 template <bool LOGN>
-__global__ void __launch_bounds__(FG_GEN_THREADS) k_gen_rows(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
-                                                              const double* __restrict__ e_planes, const float* __restrict__ lambda,
-                                                              size_t in_stride, uint32_t* __restrict__ Pg,
-                                                              const uint64_t* __restrict__ rowbase, const uint32_t* __restrict__ rowcap,
-                                                              float2* __restrict__ Gg, float* __restrict__ R2g,
-                                                              uint32_t* __restrict__ overflow, StageGeo geo, RenderConsts c) {
-    __shared__ uint16_t list[FG_GEN_TILE];
-    __shared__ __align__(16) uint32_t cnt[FG_GEN_TILE];
-    __shared__ uint32_t wsA[8], wsB[2][8], wsC[8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int row = blockIdx.x, plane = blockIdx.y;
+__global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
+                                                                const double* __restrict__ e_planes, const float* __restrict__ lambda,
+                                                                size_t in_stride, uint32_t* __restrict__ Pg,
+                                                                const uint64_t* __restrict__ rowbase, const uint32_t* __restrict__ rowcap,
+                                                                float2* __restrict__ Gg, float* __restrict__ R2g,
+                                                                uint32_t* __restrict__ overflow, StageGeo geo, int n_planes, RenderConsts c) {
+    __shared__ GenWarpSmem sm_all[FG_GW_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    GenWarpSmem& sm = sm_all[warp];
+    const size_t ridx = (size_t)blockIdx.x * FG_GW_WARPS + warp;
+    if (ridx >= (size_t)geo.rows * n_planes) return; // whole warp
+    const int plane = (int)(ridx / geo.rows), row = (int)(ridx - (size_t)plane * geo.rows);
     const int j = geo.j0 + row;
     const float sy = __fmul_rn(__int2float_rn(j), c.delta);
     const int iy = min(max(floor_i32(sy), 0), c.in_h - 1);
     const double* erow = e_planes + in_stride * plane + (size_t)iy * c.in_w;
     const float* lrow = lambda + in_stride * plane + (size_t)iy * c.in_w;
     const uint32_t* bmrow = bm_planes + bm_plane_words * plane + (size_t)row * geo.pitchw;
-    const size_t ridx = (size_t)plane * geo.rows + row;
     const uint64_t base = rowbase[ridx];
     const uint32_t cap = rowcap[ridx];
     uint32_t* prow = Pg + ridx * geo.ppitch;
-    uint32_t run = 0; // grains of the row written so far
-    int batch_par = 0;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t run = 0; // grains of the row placed so far
+    uint32_t qn = 0;  // parked cells
 
     auto warp_incl = [&](uint32_t v) {
 #pragma unroll
@@ -138,44 +152,60 @@ __global__ void __launch_bounds__(FG_GEN_THREADS) k_gen_rows(const uint32_t* __r
         }
         return v;
     };
-    // sum and exclusive offset of this warp from eight warp totals in shared memory
-    auto block_off = [&](const uint32_t* ws, uint32_t& total) {
-        const uint32_t v = (lane < 8) ? ws[lane] : 0u;
-        const uint32_t wi = warp_incl(v);
-        total = __shfl_sync(0xFFFFFFFFu, wi, 7);
-        return __shfl_sync(0xFFFFFFFFu, wi - v, warp);
+    auto draw_grains = [&](Xoshiro& rng, float sx, uint64_t dst, uint32_t q) {
+        for (uint32_t g = 0; g < q; ++g) {
+            const float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
+            const float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
+            Gg[dst + g] = make_float2(cx, cy);
+            if (LOGN) { // RadiusProfile::sample + clamp (src/model.rs:137-148, src/pixelwise.rs:89-95)
+                const float radius = radius_sample_clamped(c.rad, rng);
+                R2g[dst + g] = radius > 0.0f ? __fmul_rn(radius, radius) : -1.0f;
+            }
+        }
+    };
+    auto flush = [&]() {
+        __syncwarp();
+        for (uint32_t b = 0; b < qn; b += 32) {
+            const uint32_t t = b + lane;
+            if (t < qn) {
+                Xoshiro rng;
+                rng.s0 = sm.q_s0[t]; rng.s1 = sm.q_s1[t]; rng.s2 = sm.q_s2[t]; rng.s3 = sm.q_s3[t];
+                draw_grains(rng, sm.q_sx[t], sm.q_dst[t], sm.q_q[t]);
+            }
+        }
+        qn = 0;
+        __syncwarp();
     };
 
-    for (int tile0 = 0; tile0 < (int)geo.ppitch; tile0 += FG_GEN_TILE) {
+    for (int tile0 = 0; tile0 < (int)geo.ppitch; tile0 += FG_GW_TILE) {
         // ---- a: clear the counts, compact the tile's non-empty cells into `list` ----
         {
-            uint4* cz = (uint4*)cnt;
-            cz[tid] = make_uint4(0, 0, 0, 0);
-            cz[tid + FG_GEN_THREADS] = make_uint4(0, 0, 0, 0);
+            uint4* cz = (uint4*)sm.cnt; // 2 KiB = 128 x 16 B
+#pragma unroll
+            for (int k = 0; k < FG_GW_TILE * 2 / 16 / 32; ++k) cz[lane + 32 * k] = make_uint4(0, 0, 0, 0);
         }
-        const uint32_t widx = (uint32_t)(tile0 >> 5) + (uint32_t)(tid >> 2), sh = 8u * (tid & 3);
-        const uint32_t word = widx < geo.pitchw ? __ldg(bmrow + widx) : 0u;
-        uint32_t bits = (word >> sh) & 0xFFu;
+        const uint32_t widx = (uint32_t)(tile0 >> 5) + (uint32_t)lane;
+        uint32_t bits = widx < geo.pitchw ? __ldg(bmrow + widx) : 0u;
         const uint32_t nb = __popc(bits);
         const uint32_t inclA = warp_incl(nb);
-        if (lane == 31) wsA[warp] = inclA;
-        __syncthreads();
-        uint32_t M;
-        uint32_t pos = block_off(wsA, M) + inclA - nb;
-        while (bits) {
-            const int b0 = __ffs(bits) - 1;
-            bits &= bits - 1;
-            list[pos++] = (uint16_t)((tid >> 2) * 32 + (int)sh + b0);
+        const uint32_t M = __shfl_sync(0xFFFFFFFFu, inclA, 31);
+        {
+            uint32_t pos = inclA - nb;
+            while (bits) {
+                const int b0 = __ffs(bits) - 1;
+                bits &= bits - 1;
+                sm.list[pos++] = (uint16_t)(lane * 32 + b0);
+            }
         }
-        __syncthreads();
-        // ---- b: dense batches, one thread per non-empty cell ----
-        for (uint32_t b0 = 0; b0 < M; b0 += FG_GEN_THREADS) {
-            const uint32_t t = b0 + tid;
+        __syncwarp();
+        // ---- b: 32 non-empty cells at a time ----
+        for (uint32_t b0 = 0; b0 < M; b0 += 32) {
+            const uint32_t t = b0 + lane;
             uint32_t q = 0, cl = 0;
             Xoshiro rng;
             float sx = 0.0f;
             if (t < M) {
-                cl = list[t];
+                cl = sm.list[t];
                 const int i = geo.i0 + tile0 + (int)cl;
                 sx = __fmul_rn(__int2float_rn(i), c.delta);
                 const int ix = min(max(floor_i32(sx), 0), c.in_w - 1);
@@ -190,55 +220,65 @@ __global__ void __launch_bounds__(FG_GEN_THREADS) k_gen_rows(const uint32_t* __r
                 }
             }
             const uint32_t inclB = warp_incl(q);
-            uint32_t* ws = wsB[batch_par];
-            batch_par ^= 1;
-            if (lane == 31) ws[warp] = inclB;
-            __syncthreads();
-            uint32_t total;
-            const uint32_t off = block_off(ws, total) + inclB - q;
-            if ((uint64_t)run + total > cap) { // uniform
-                if (tid == 0) atomicExch(overflow, 1u);
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inclB, 31);
+            if ((uint64_t)run + total > cap || __any_sync(0xFFFFFFFFu, q > 65535u)) { // uniform
+                if (lane == 0) atomicExch(overflow, 1u);
                 return;
             }
-            if (t < M) {
-                cnt[cl] = q;
-                const uint64_t idx = base + run + off;
-                for (uint32_t g = 0; g < q; ++g) {
-                    const float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
-                    const float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
-                    Gg[idx + g] = make_float2(cx, cy);
-                    if (LOGN) { // RadiusProfile::sample + clamp (src/model.rs:137-148, src/pixelwise.rs:89-95)
-                        const float radius = radius_sample_clamped(c.rad, rng);
-                        R2g[idx + g] = radius > 0.0f ? __fmul_rn(radius, radius) : -1.0f;
-                    }
-                }
+            const uint64_t dst = base + run + (inclB - q);
+            if (q) sm.cnt[cl] = (uint16_t)q;
+            const bool parked = q >= 2u;
+            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, parked);
+            if (q == 1u) draw_grains(rng, sx, dst, 1u);
+            if (parked) {
+                const uint32_t slot = qn + __popc(pm & lt_mask);
+                sm.q_s0[slot] = rng.s0; sm.q_s1[slot] = rng.s1; sm.q_s2[slot] = rng.s2; sm.q_s3[slot] = rng.s3;
+                sm.q_dst[slot] = dst;
+                sm.q_q[slot] = q;
+                sm.q_sx[slot] = sx;
             }
+            qn += __popc(pm);
+            if (qn > FG_GW_QCAP - 32) flush();
             run += total;
         }
-        __syncthreads(); // cnt complete
-        // ---- c: prefix entries of the tile's cells ----
+        __syncwarp(); // cnt complete
+        // ---- c: prefix entries of the tile's cells: lane l owns cells 32 l .. 32 l + 31 ----
         {
-            const uint4 c0 = ((const uint4*)cnt)[2 * tid], c1 = ((const uint4*)cnt)[2 * tid + 1];
-            const uint32_t s8 = c0.x + c0.y + c0.z + c0.w + c1.x + c1.y + c1.z + c1.w;
-            const uint32_t inclC = warp_incl(s8);
-            if (lane == 31) wsC[warp] = inclC;
-            __syncthreads();
-            uint32_t total;
-            // grains before this tile = run - (tile total)
-            uint32_t p0 = block_off(wsC, total) + inclC - s8;
-            p0 += run - total;
-            const int k0 = tile0 + 8 * tid;
-            if (k0 < (int)geo.ppitch) {
+            const uint4* cs = (const uint4*)(sm.cnt + 32 * lane);
+            uint4 v[4];
+            uint32_t s32 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[k] = cs[k];
+                s32 += (v[k].x & 0xFFFFu) + (v[k].x >> 16) + (v[k].y & 0xFFFFu) + (v[k].y >> 16) + (v[k].z & 0xFFFFu) + (v[k].z >> 16) +
+                       (v[k].w & 0xFFFFu) + (v[k].w >> 16);
+            }
+            const uint32_t inclC = warp_incl(s32);
+            const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, inclC, 31);
+            uint32_t pacc = run - tile_total + inclC - s32; // grains of the row before this lane's first cell
+            const int k0 = tile0 + 32 * lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
                 uint4 o0, o1;
-                o0.x = p0; o0.y = o0.x + c0.x; o0.z = o0.y + c0.y; o0.w = o0.z + c0.z;
-                o1.x = o0.w + c0.w; o1.y = o1.x + c1.x; o1.z = o1.y + c1.y; o1.w = o1.z + c1.z;
-                uint4* dst = (uint4*)(prow + k0);
-                dst[0] = o0;
-                dst[1] = o1;
+                o0.x = pacc; pacc += w[0] & 0xFFFFu;
+                o0.y = pacc; pacc += w[0] >> 16;
+                o0.z = pacc; pacc += w[1] & 0xFFFFu;
+                o0.w = pacc; pacc += w[1] >> 16;
+                o1.x = pacc; pacc += w[2] & 0xFFFFu;
+                o1.y = pacc; pacc += w[2] >> 16;
+                o1.z = pacc; pacc += w[3] & 0xFFFFu;
+                o1.w = pacc; pacc += w[3] >> 16;
+                if (k0 + 8 * k < (int)geo.ppitch) { // ppitch is a multiple of 8
+                    uint4* dstp = (uint4*)(prow + k0 + 8 * k);
+                    dstp[0] = o0;
+                    dstp[1] = o1;
+                }
             }
         }
-        __syncthreads(); // cnt / list / wsA are rewritten by the next tile
+        __syncwarp(); // cnt / list are rewritten by the next tile
     }
+    flush();
 }
 
 } // namespace fg

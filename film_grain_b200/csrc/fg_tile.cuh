@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ la
 // one thread per cell column; each warp
 // stores one aligned 32-bit word per plane.
 #define FG_BM_ROWS 16 // cell rows per thread in k_first_draw_bitmap (amortises the column half of the hash)
+template <int SEEDING> // compile-time: a run-time select gets if-converted and issues both seeders
 __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __restrict__ thr_planes, size_t in_stride,
                                                             int n_planes, uint32_t* __restrict__ bm, size_t bm_plane_words,
                                                             int i0, int j0, int cols, int rows, uint32_t pitchw, RenderConsts c) {
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __res
         if (valid) {
             const uint64_t h = mix3_row(hcol, j);
             uint64_t s0, s3;
-            if (c.seeding == 0) { s0 = pcg_word_pair<0>(h); s3 = pcg_word_pair<3>(h); }
+            if (SEEDING == 0) { s0 = pcg_word_pair<0>(h); s3 = pcg_word_pair<3>(h); }
             else { Xoshiro t; seed_splitmix(t, h); s0 = t.s0; s3 = t.s3; }
             m1 = (rotl64(s0 + s3, 23) + s0) >> 11;
             const int iy = min(max(floor_i32(__fmul_rn(__int2float_rn(j), c.delta)), 0), c.in_h - 1);
@@ -955,8 +956,12 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
     {
         dim3 bgrid((unsigned)((g.bm_rows + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
-        k_first_draw_bitmap<<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, g.bm_cols,
-                                                  g.bm_rows, g.bm_pitchw, c);
+        if (c.seeding == 0)
+            k_first_draw_bitmap<0><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, g.bm_cols,
+                                                         g.bm_rows, g.bm_pitchw, c);
+        else
+            k_first_draw_bitmap<1><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, g.bm_cols,
+                                                         g.bm_rows, g.bm_pitchw, c);
         FG_CUDA(ctx, cudaGetLastError());
     }
     ctx->stats.launches += 2;
@@ -989,13 +994,13 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         float2* d_G = (float2*)ctx->gtab.p;
         float* d_R2 = (float*)((unsigned char*)ctx->gtab.p + g_bytes);
         StageGeo geo{g.bm_i0, g.bm_j0, g.bm_cols, g.bm_rows, g.bm_pitchw, g.ppitch};
-        const dim3 ggrid((unsigned)g.bm_rows, (unsigned)n_planes);
+        const unsigned ggrid = (unsigned)((n_rows_all + FG_GW_WARPS - 1) / FG_GW_WARPS);
         if (c.rad.lognorm)
-            k_gen_rows<true><<<ggrid, FG_GEN_THREADS, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
-                                                               d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, c);
+            k_gen_rows<true><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
+                                                               d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, n_planes, c);
         else
-            k_gen_rows<false><<<ggrid, FG_GEN_THREADS, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
-                                                                d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, c);
+            k_gen_rows<false><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
+                                                                d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, n_planes, c);
         FG_CUDA(ctx, cudaGetLastError());
         uint32_t overflow = 0;
         FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));
