@@ -25,6 +25,7 @@
 // overflow, log-normal radii, exotic geometry) is appended to a fallback list and rendered by the
 // general direct kernel (fg_kernels.cuh) in the same call: results are identical either way.
 #pragma once
+#include <cstdlib>
 #include "fg_ctx.cuh"
 #include "fg_kernels.cuh"
 #include "fg_stage.cuh"
@@ -178,6 +179,23 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
     float2 v;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
     return v;
+}
+
+// squared distance with the packed f32x2 pipe: (dx, dy) = p - g and (dx*dx, dy*dy) are one instruction
+// each (FADD2 / FMUL2, round-to-nearest per element like the scalar forms), then dx*dx + dy*dy.
+__device__ __forceinline__ float dist2_packed(uint64_t p, float2 g) {
+    uint64_t gg, d, s;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(gg) : "f"(g.x), "f"(g.y));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(p), "l"(gg));
+    asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(s) : "l"(d));
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(s));
+    return __fadd_rn(lo, hi);
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float x, float y) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
 }
 
 // packed byte offsets of P[row][i0 - i_lo] and P[row][i1 - i_lo + 1] for sample abscissa xg (0 = no cells).
@@ -347,70 +365,110 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
         }
 
         // =================== STAGED: load cell rows j_gen .. j_hi from the cell table ===================
+        // Rows are placed LINEARLY in the grain ring: a row that would cross the end of the ring starts
+        // at 0 instead (the tail is skipped), so within a row end >= start and the evaluation needs no
+        // wrap arithmetic.  The two first prefix rows are mirrored behind the last one for the same reason.
         if (STAGED && j_gen <= j_hi) {
             const int nn = j_hi - j_gen + 1; // <= RH
             uint32_t* rowN = rowA + RH;
             uint32_t* rowH = rowN + RH;
             const size_t trow0 = (size_t)plane * cfg.bm_rows + (size_t)(j_gen - cfg.bm_j0);
             const uint32_t tcol0 = (uint32_t)(i_lo - cfg.bm_i0);
-            for (int t = tid; t < nn; t += FG_TILE_THREADS) {
-                const uint32_t* pr = tab.Pg + (trow0 + t) * cfg.ppitch + tcol0;
-                const uint32_t a = __ldg(pr), b = __ldg(pr + CW);
-                rowA[t] = a;
-                rowN[t] = b - a;
-            }
-            __syncthreads();
-            if (warp == 0) { // ring position of every row's first grain
-                uint32_t carry = head;
+            // Every warp computes the placement of ALL new rows itself (same loads, same scan, same
+            // verdict) and writes the same values to rowA/rowN/rowH: no CTA barrier, no exchange.
+            uint32_t nhead;
+            {
+                const bool live = j_lo < j_gen;             // rows of earlier steps still in the window
+                uint32_t cur = live ? head : 0u;            // empty ring: restart at 0
+                const uint32_t tail = live ? (uint32_t)P[rr_lo * PS] : 0u;
+                const bool wrapped0 = cur < tail;           // live region already wraps around the end
+                bool wrapped = false, bad = false;
                 for (int t0 = 0; t0 < nn; t0 += 32) {
-                    const uint32_t v = (t0 + lane < nn) ? rowN[t0 + lane] : 0u;
+                    uint32_t a = 0, v = 0;
+                    if (t0 + lane < nn) {
+                        const uint32_t* pr = tab.Pg + (trow0 + t0 + lane) * cfg.ppitch + tcol0;
+                        a = __ldg(pr);
+                        v = __ldg(pr + CW) - a;
+                    }
                     uint32_t incl = v;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
                         const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
                         if (lane >= d) incl += u;
                     }
-                    if (t0 + lane < nn) rowH[t0 + lane] = carry + incl - v; // not yet reduced mod GC
-                    carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    const uint32_t excl = incl - v, tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    uint32_t pos = cur + excl;
+                    const uint32_t over = __ballot_sync(0xFFFFFFFFu, pos + v > GC);
+                    if (over) { // the first row that does not fit before the end restarts at 0
+                        const int f = __ffs(over) - 1;
+                        const uint32_t eb = __shfl_sync(0xFFFFFFFFu, excl, f);
+                        if (lane >= f) pos = excl - eb;
+                        if (wrapped || wrapped0) bad = true; // second wrap: cannot fit
+                        wrapped = true;
+                        cur = tot - eb;
+                        if (cur > GC) bad = true;
+                    } else {
+                        cur += tot;
+                    }
+                    if (t0 + lane < nn) { rowA[t0 + lane] = a; rowN[t0 + lane] = v; rowH[t0 + lane] = pos; }
                 }
-                if (lane == 0) wtot[0] = carry - head;
+                // the new rows must end strictly before the oldest live grain
+                if ((wrapped || wrapped0) && cur >= tail) bad = true;
+                nhead = bad ? 0xFFFFFFFFu : cur;
             }
-            __syncthreads();
-            const uint32_t total = wtot[0];
-            if (used + total >= GC) { // uniform: grain ring overflow (== GC would alias an empty ring)
+            if (nhead == 0xFFFFFFFFu) { // uniform: the window does not fit the grain ring
                 if (tid == 0) push_fallback(fb_list, fb_count, fb_cap, X0, ya, X1 - X0 + 1, Y1 - ya, plane);
                 return;
             }
+            __syncwarp();
             for (int t = warp; t < nn; t += FG_TILE_WARPS) {
-                const uint32_t a = rowA[t], n = rowN[t];
-                uint32_t h = rowH[t]; // < 2 * GC
-                if (h >= GC) h -= GC;
+                const uint32_t a = rowA[t], n = rowN[t], h = rowH[t];
                 int rr = rr_gen + t;
                 if (rr >= RH) rr -= RH;
                 const uint32_t* pr = tab.Pg + (trow0 + t) * cfg.ppitch + tcol0;
-                uint16_t* prow = P + rr * PS;
-                for (int ci = lane; ci < CW1; ci += 32) {
-                    uint32_t v = __ldg(pr + ci) - a + h;
-                    if (v >= GC) v -= GC;
-                    prow[ci] = (uint16_t)v;
-                }
                 const size_t gsrc = (size_t)__ldg(tab.rowbase + trow0 + t) + a;
-                for (uint32_t k = lane; k < n; k += 32) {
-                    uint32_t pos = h + k;
-                    if (pos >= GC) pos -= GC;
-                    const float2 gr = __ldg(tab.Gg + gsrc + k);
-                    G[pos] = gr;
-                    if (pos < FG_TILE_GPAD) G[GC + pos] = gr; // mirror: unrolled reads never wrap
-                    if (LOGN) {
-                        const float rr2 = __ldg(tab.R2g + gsrc + k);
-                        R2[pos] = rr2;
-                        if (pos < FG_TILE_GPAD) R2[GC + pos] = rr2;
+                uint16_t* prow = P + rr * PS;
+                uint16_t* pmir = P + (rr + RH) * PS; // rows 0 and 1 again behind row RH - 1
+                // loads first (eight in flight per lane), then the stores
+                for (int c0 = 0; c0 < CW1; c0 += 256) {
+                    uint32_t pv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int ci = c0 + 32 * k + lane;
+                        pv[k] = ci < CW1 ? __ldg(pr + ci) : 0u;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int ci = c0 + 32 * k + lane;
+                        if (ci < CW1) {
+                            const uint16_t v = (uint16_t)(pv[k] - a + h);
+                            prow[ci] = v;
+                            if (rr < 2) pmir[ci] = v;
+                        }
+                    }
+                }
+                for (uint32_t k0 = 0; k0 < n; k0 += 128) {
+                    float2 gv[4];
+                    float rv[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t kk = k0 + 32 * k + lane;
+                        if (kk < n) {
+                            gv[k] = __ldg(tab.Gg + gsrc + kk);
+                            if (LOGN) rv[k] = __ldg(tab.R2g + gsrc + kk);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t kk = k0 + 32 * k + lane;
+                        if (kk < n) {
+                            G[h + kk] = gv[k];
+                            if (LOGN) R2[h + kk] = rv[k];
+                        }
                     }
                 }
             }
-            head += total;
-            if (head >= GC) head -= GC;
-            used += total;
+            head = nhead;
             j_gen += nn;
             rr_gen += nn;
             if (rr_gen >= RH) rr_gen -= RH;
@@ -661,24 +719,29 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                             // list of n = n0 + n1 + n2 grains (slot u -> row by two compares), FG_TILE_U3
                             // predicated slots folded into a running minimum, then an early-exit remainder.
                             uint32_t o1A = offA + PS2, o1B = offB + PS2;
-                            if (o1A >= Ps + RHPS2) o1A -= RHPS2;
-                            if (o1B >= Ps + RHPS2) o1B -= RHPS2;
                             uint32_t o2A = o1A + PS2, o2B = o1B + PS2;
-                            if (o2A >= Ps + RHPS2) o2A -= RHPS2;
-                            if (o2B >= Ps + RHPS2) o2B -= RHPS2;
+                            if (!STAGED) { // STAGED: the first two prefix rows are mirrored behind the last
+                                if (o1A >= Ps + RHPS2) o1A -= RHPS2;
+                                if (o1B >= Ps + RHPS2) o1B -= RHPS2;
+                                o2A = o1A + PS2; o2B = o1B + PS2;
+                                if (o2A >= Ps + RHPS2) o2A -= RHPS2;
+                                if (o2B >= Ps + RHPS2) o2B -= RHPS2;
+                            }
                             const uint32_t s0A = lds_u16(offA + a2A), e0A = lds_u16(offA + b2A);
                             const uint32_t s0B = lds_u16(offB + a2B), e0B = lds_u16(offB + b2B);
                             const uint32_t s1A = lds_u16(o1A + a2A), e1A = lds_u16(o1A + b2A);
                             const uint32_t s1B = lds_u16(o1B + a2B), e1B = lds_u16(o1B + b2B);
                             const uint32_t s2A = lds_u16(o2A + a2A), e2A = lds_u16(o2A + b2A);
                             const uint32_t s2B = lds_u16(o2B + a2B), e2B = lds_u16(o2B + b2B);
-                            const uint32_t c1A = e0A - s0A + (e0A < s0A ? GC : 0u), c1B = e0B - s0B + (e0B < s0B ? GC : 0u);
-                            const uint32_t c2A = c1A + e1A - s1A + (e1A < s1A ? GC : 0u), c2B = c1B + e1B - s1B + (e1B < s1B ? GC : 0u);
-                            const uint32_t nA = c2A + e2A - s2A + (e2A < s2A ? GC : 0u), nB = c2B + e2B - s2B + (e2B < s2B ? GC : 0u);
+                            // STAGED rows never wrap inside the ring: end >= start
+                            const uint32_t c1A = e0A - s0A + ((!STAGED && e0A < s0A) ? GC : 0u), c1B = e0B - s0B + ((!STAGED && e0B < s0B) ? GC : 0u);
+                            const uint32_t c2A = c1A + e1A - s1A + ((!STAGED && e1A < s1A) ? GC : 0u), c2B = c1B + e1B - s1B + ((!STAGED && e1B < s1B) ? GC : 0u);
+                            const uint32_t nA = c2A + e2A - s2A + ((!STAGED && e2A < s2A) ? GC : 0u), nB = c2B + e2B - s2B + ((!STAGED && e2B < s2B) ? GC : 0u);
                             const uint32_t t1A = s1A - c1A, t2A = s2A - c2A, t1B = s1B - c1B, t2B = s2B - c2B; // mod 2^32
+                            const uint64_t pA = pack_f32x2(xgA, ygA), pB = pack_f32x2(xgB, ygB);
                             float2 gA[FG_TILE_U3], gB[FG_TILE_U3];
 #pragma unroll
-                            for (int u = 0; u < FG_TILE_U3; ++u) { // past n: stale but in-bounds (mirror pad)
+                            for (int u = 0; u < FG_TILE_U3; ++u) { // past n: stale but in-bounds (pad behind the ring)
                                 const uint32_t iA = ((uint32_t)u < c1A ? s0A : ((uint32_t)u < c2A ? t1A : t2A)) + (uint32_t)u;
                                 const uint32_t iB = ((uint32_t)u < c1B ? s0B : ((uint32_t)u < c2B ? t1B : t2B)) + (uint32_t)u;
                                 gA[u] = lds_f32x2(Gs + iA * 8u);
@@ -686,21 +749,16 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                             }
 #pragma unroll
                             for (int u = 0; u < FG_TILE_U3; ++u) {
-                                const float gxA = ((uint32_t)u < nA) ? gA[u].x : __int_as_float(0x7f800000);
-                                const float gxB = ((uint32_t)u < nB) ? gB[u].x : __int_as_float(0x7f800000);
-                                const float dxA = __fsub_rn(xgA, gxA), dyA = __fsub_rn(ygA, gA[u].y);
-                                const float dxB = __fsub_rn(xgB, gxB), dyB = __fsub_rn(ygB, gB[u].y);
-                                dminA = fminf(dminA, __fadd_rn(__fmul_rn(dxA, dxA), __fmul_rn(dyA, dyA)));
-                                dminB = fminf(dminB, __fadd_rn(__fmul_rn(dxB, dxB), __fmul_rn(dyB, dyB)));
+                                const float dA = dist2_packed(pA, gA[u]), dB = dist2_packed(pB, gB[u]);
+                                dminA = fminf(dminA, ((uint32_t)u < nA) ? dA : __int_as_float(0x7f800000));
+                                dminB = fminf(dminB, ((uint32_t)u < nB) ? dB : __int_as_float(0x7f800000));
                             }
                             if (nA > FG_TILE_U3 && !(dminA <= r2)) { // remainder: exits on the first hit
                                 uint32_t u = FG_TILE_U3;
                                 do {
                                     uint32_t gi = (u < c1A ? s0A : (u < c2A ? t1A : t2A)) + u;
-                                    if (gi >= GC) gi -= GC;
-                                    const float2 gr = lds_f32x2(Gs + gi * 8u);
-                                    const float dx = __fsub_rn(xgA, gr.x), dy = __fsub_rn(ygA, gr.y);
-                                    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    if (!STAGED && gi >= GC) gi -= GC;
+                                    const float d2 = dist2_packed(pA, lds_f32x2(Gs + gi * 8u));
                                     if (d2 <= r2) { dminA = d2; break; }
                                 } while (++u < nA);
                             }
@@ -708,10 +766,8 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                                 uint32_t u = FG_TILE_U3;
                                 do {
                                     uint32_t gi = (u < c1B ? s0B : (u < c2B ? t1B : t2B)) + u;
-                                    if (gi >= GC) gi -= GC;
-                                    const float2 gr = lds_f32x2(Gs + gi * 8u);
-                                    const float dx = __fsub_rn(xgB, gr.x), dy = __fsub_rn(ygB, gr.y);
-                                    const float d2 = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+                                    if (!STAGED && gi >= GC) gi -= GC;
+                                    const float d2 = dist2_packed(pB, lds_f32x2(Gs + gi * 8u));
                                     if (d2 <= r2) { dminB = d2; break; }
                                 } while (++u < nB);
                             }
@@ -780,7 +836,9 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             if (X0 + xl <= X1) outp[(size_t)(ya + yl) * c.out_w + X0 + xl] = __fmul_rn((float)pcount[p], c.inv_samples);
             pcount[p] = 0;
         }
-        __syncthreads();
+        // STAGED: the loader of the next step touches neither pcount nor wpair, and the barrier that
+        // ends it orders these stores before the next evaluation
+        if (!STAGED) __syncthreads();
     }
 }
 
@@ -816,8 +874,10 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     // overflows into the fallback list at run time.
     for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
         static const int th_candidates[] = {32, 24, 16, 12, 8, 6, 4, 3, 2, 1};
+        static const int th_forced = std::getenv("FG_B200_TH") ? std::atoi(std::getenv("FG_B200_TH")) : 0; // experiments
         for (int TH : th_candidates) {
             if (pl.ok) break;
+            if (th_forced > 0 && TH != th_forced) continue;
             if (TH > 1 && TH > 2 * band) continue;
             const double rhb = ((TH - 1) * inv_zoom + oy + 2.0 * rm) / delta + 4.0;
             if (!(rhb < 30000.0)) continue;
@@ -826,7 +886,7 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
             g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R;
             uint32_t off = 0;
             g.off_col = off; off = align_up(off + (staged ? 0u : (uint32_t)CWB * 16u), 16);
-            g.off_P = off; off = align_up(off + (uint32_t)RH * PS * 2u, 16);
+            g.off_P = off; off = align_up(off + (uint32_t)(RH + (staged ? 2 : 0)) * PS * 2u, 16);
             g.off_list = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
             g.off_E = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
             g.off_cnt = off; off = align_up(off + (staged ? 0u : (uint32_t)(FG_TILE_NE + 8) * 4u), 16);
@@ -1029,6 +1089,9 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
                                                  chunks, d_fbtotal, c);
     FG_CUDA(ctx, cudaGetLastError());
     ctx->stats.launches += 2;
+    if (std::getenv("FG_B200_DEBUG"))
+        std::fprintf(stderr, "[fg] band %d..%d staged=%d TH=%d SEG=%d RH=%d CWB=%d GCAP=%d smem=%u units=%u\n", c.row_begin, c.row_end,
+                     (int)staged, g.TH, g.SEG, g.RH, g.CWB, g.GCAP, g.total, units);
     ctx->stats.tiles_total += units;
     ctx->strip_launches += 1;
     return FG_OK;
