@@ -123,6 +123,7 @@ struct TileCfg {
     int bm_cols, bm_rows; // its extent in cells
     uint32_t bm_pitchw;   // 32-bit words per bitmap row
     uint32_t ppitch;      // staged mode: cell-table prefix entries per row
+    float r2c;            // constant radius: squared clamped radius (src/pixelwise.rs:89-97)
     uint32_t off_col, off_P, off_G, off_R2, off_list, off_E, off_cnt, off_wtot, off_pcount, off_wpair, off_rows, total;
 };
 
@@ -248,7 +249,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
     const double* ev = e_planes + in_stride * plane;
     float* outp = out + out_stride * plane;
     const float rm = c.rad.rm, delta = c.delta;
-    const float r2 = __fmul_rn(c.rad.mean_linear > rm ? rm : c.rad.mean_linear, c.rad.mean_linear > rm ? rm : c.rad.mean_linear);
+    const float r2 = cfg.r2c; // min(mean radius, rm)^2, squared on the host in f32
     const bool radius_ok = LOGN || (c.rad.mean_linear > rm ? rm : c.rad.mean_linear) > 0.0f; // const radius <= 0: grains never cover
     const uint32_t GC = (uint32_t)cfg.GCAP;
 
@@ -263,6 +264,9 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
         return;
     }
     const int CW = (int)CWl, CW1 = CW + 1;
+    // STAGED: prefix rows are stored from the table column rounded down to a multiple of four (16-byte
+    // vector loads); logical window column c lives at index c + sh
+    const int sh = STAGED ? ((i_lo - cfg.bm_i0) & 3) : 0;
     const int PS = cfg.PS, RH = cfg.RH;
 
     if (!STAGED)
@@ -302,10 +306,12 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             if (k < c.n && xvalid) {
                 float2 o = __ldg(offsets_input + k);
                 xg = __fsub_rn(bx, o.x);
-                ip = col_range_packed(xg, rm, delta, i_lo);
+                ip = col_range_packed(xg, rm, delta, i_lo - sh);
             }
             xg_r[s] = xg;
-            ip_r[s] = ip;
+            // no cells / inactive lane: an empty range at the first VALID prefix entry (entries below
+            // the column shift hold junk)
+            ip_r[s] = ip ? ip : (uint32_t)(2 * sh) * 0x10001u;
         }
     };
     bool xk_loaded = false;
@@ -380,7 +386,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             {
                 const bool live = j_lo < j_gen;             // rows of earlier steps still in the window
                 uint32_t cur = live ? head : 0u;            // empty ring: restart at 0
-                const uint32_t tail = live ? (uint32_t)P[rr_lo * PS] : 0u;
+                const uint32_t tail = live ? (uint32_t)P[rr_lo * PS + sh] : 0u;
                 const bool wrapped0 = cur < tail;           // live region already wraps around the end
                 bool wrapped = false, bad = false;
                 for (int t0 = 0; t0 < nn; t0 += 32) {
@@ -425,25 +431,29 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                 const uint32_t a = rowA[t], n = rowN[t], h = rowH[t];
                 int rr = rr_gen + t;
                 if (rr >= RH) rr -= RH;
-                const uint32_t* pr = tab.Pg + (trow0 + t) * cfg.ppitch + tcol0;
+                const uint4* pr4 = (const uint4*)(tab.Pg + (trow0 + t) * cfg.ppitch + (tcol0 - (uint32_t)sh));
                 const size_t gsrc = (size_t)__ldg(tab.rowbase + trow0 + t) + a;
-                uint16_t* prow = P + rr * PS;
-                uint16_t* pmir = P + (rr + RH) * PS; // rows 0 and 1 again behind row RH - 1
-                // loads first (eight in flight per lane), then the stores
-                for (int c0 = 0; c0 < CW1; c0 += 256) {
-                    uint32_t pv[8];
+                uint2* prow = (uint2*)(P + rr * PS);
+                uint2* pmir = (uint2*)(P + (rr + RH) * PS); // rows 0 and 1 again behind row RH - 1
+                const int n4 = (CW1 + sh + 3) >> 2;
+                const uint32_t adj = h - a;
+                // loads first (two 16-byte loads in flight per lane), then the stores
+                for (int c0 = 0; c0 < n4; c0 += 64) {
+                    uint4 pv[2];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int ci = c0 + 32 * k + lane;
-                        pv[k] = ci < CW1 ? __ldg(pr + ci) : 0u;
+                    for (int k = 0; k < 2; ++k) {
+                        const int q4 = c0 + 32 * k + lane;
+                        if (q4 < n4) pv[k] = __ldg(pr4 + q4);
                     }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int ci = c0 + 32 * k + lane;
-                        if (ci < CW1) {
-                            const uint16_t v = (uint16_t)(pv[k] - a + h);
-                            prow[ci] = v;
-                            if (rr < 2) pmir[ci] = v;
+                    for (int k = 0; k < 2; ++k) {
+                        const int q4 = c0 + 32 * k + lane;
+                        if (q4 < n4) {
+                            uint2 o; // entries left of the window (index < sh) are never read
+                            o.x = ((pv[k].x + adj) & 0xFFFFu) | ((pv[k].y + adj) << 16);
+                            o.y = ((pv[k].z + adj) & 0xFFFFu) | ((pv[k].w + adj) << 16);
+                            prow[q4] = o;
+                            if (rr < 2) pmir[q4] = o;
                         }
                     }
                 }
@@ -650,7 +660,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                         jp = (uint32_t)(rr * PS * 2) | ((uint32_t)(j1 - j0 + 1) << 24);
                     }
                 }
-                wp[s * th + yl] = make_float2(yg, __uint_as_float(jp));
+                wp[yl * SPWC + s] = make_float2(yg, __uint_as_float(jp));
             }
             __syncwarp();
             if (xvalid && radius_ok) {
@@ -664,7 +674,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                         uint32_t cnt = 0;
 #pragma unroll
                         for (int s = 0; s < SPWC; ++s) {
-                            const float2 pd = wp[s * th + yl];
+                            const float2 pd = wp[yl * SPWC + s];
                             const uint32_t jp = __float_as_uint(pd.y);
                             const uint32_t a2 = ip_r[s] & 0xFFFFu, b2 = ip_r[s] >> 16;
                             const uint32_t nrow = (a2 != b2) ? (jp >> 24) : 0u;
@@ -706,11 +716,10 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                     // the arithmetic), which doubles the independent work in flight per warp.
 #pragma unroll
                     for (int s = 0; s < SPWC; s += 2) {
-                        const float2 pdA = wp[s * th + yl], pdB = wp[(s + 1) * th + yl];
+                        const float2 pdA = wp[yl * SPWC + s], pdB = wp[yl * SPWC + s + 1];
                         const uint32_t jpA = __float_as_uint(pdA.y), jpB = __float_as_uint(pdB.y);
                         const uint32_t a2A = ip_r[s] & 0xFFFFu, b2A = ip_r[s] >> 16;
                         const uint32_t a2B = ip_r[s + 1] & 0xFFFFu, b2B = ip_r[s + 1] >> 16;
-                        const uint32_t nrowA = (a2A != b2A) ? (jpA >> 24) : 0u, nrowB = (a2B != b2B) ? (jpB >> 24) : 0u;
                         uint32_t offA = Ps + (jpA & 0xFFFFFFu), offB = Ps + (jpB & 0xFFFFFFu);
                         const float xgA = xg_r[s], ygA = pdA.x, xgB = xg_r[s + 1], ygB = pdB.x;
                         float dminA = __int_as_float(0x7f800000), dminB = __int_as_float(0x7f800000);
@@ -772,6 +781,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                                 } while (++u < nB);
                             }
                         } else {
+                        const uint32_t nrowA = (a2A != b2A) ? (jpA >> 24) : 0u, nrowB = (a2B != b2B) ? (jpB >> 24) : 0u;
                         const uint32_t nmax = max(nrowA, nrowB);
 #pragma unroll 1
                         for (uint32_t r = 0; r < nmax; ++r) {
@@ -862,7 +872,7 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     if (!(cwb < 2040.0)) return pl;
     if (!(2.0 * rm / delta + 3.0 < 250.0)) return pl;   // cell rows per sample are packed in 8 bits
     const int CWB = (int)cwb;
-    const int PS = CWB + 2;
+    const int PS = staged ? (CWB + 8 + 3) / 4 * 4 : CWB + 2; // staged: + column shift (<= 3) + vector tail (<= 3), multiple of 4
     const int R = std::max(1, std::min(15, FG_TILE_CELLS / (CWB + 1)));
     const int spwc = p->n_samples <= 4u * FG_TILE_WARPS ? 4 : (p->n_samples <= 8u * FG_TILE_WARPS ? 8 : FG_TILE_SPW_MAX);
     const int band = c.row_end - c.row_begin;
@@ -993,6 +1003,8 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         g.bm_cols = (int)(i1 - i0 + 1.0); g.bm_rows = (int)(j1 - j0 + 1.0);
         g.bm_pitchw = (uint32_t)((g.bm_cols + 31) / 32);
         g.ppitch = (uint32_t)((g.bm_cols + 1 + 7) / 8 * 8);
+        const float rcl = c.rad.mean_linear > c.rad.rm ? c.rad.rm : c.rad.mean_linear;
+        g.r2c = rcl * rcl;
     }
     const size_t bm_plane_words = (size_t)g.bm_rows * g.bm_pitchw;
     if (bm_plane_words * (size_t)n_planes * 4 > ((size_t)12 << 30) || g.bm_pitchw * 32u / 256u + 1u > 65535u) return 1;
