@@ -36,7 +36,8 @@ class FgStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
                 ("launches", C.c_uint32), ("tiles_total", C.c_uint32), ("tiles_fallback", C.c_uint32),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-                ("strip_ms", C.c_float), ("strip_launches", C.c_uint32)]
+                ("strip_ms", C.c_float), ("strip_launches", C.c_uint32),
+                ("table_ms", C.c_float), ("reserved", C.c_uint32)]
 
 
 class FghParams(C.Structure):

@@ -337,6 +337,8 @@ void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) out->strip_ms = ms;
         else cudaGetLastError();
+        if (cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[4]) == cudaSuccess) out->table_ms = ms;
+        else cudaGetLastError();
     }
 }
 uint64_t fg_context_stream(const fg_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }

@@ -26,7 +26,7 @@ struct DevBuf {
 struct fg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
+    cudaEvent_t ev[7] = {};
     std::mutex mu;
     std::string err;
     const volatile int* cancel = nullptr;

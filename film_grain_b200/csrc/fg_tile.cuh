@@ -664,7 +664,11 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             }
             __syncwarp();
             if (xvalid && radius_ok) {
-                const uint32_t Ps = (uint32_t)__cvta_generic_to_shared(P), Gs = (uint32_t)__cvta_generic_to_shared(G);
+                // shared-window addresses, pinned in registers (left to itself the compiler re-derives
+                // them from the CTA id and the parameter block for every sample pair)
+                uint32_t Ps = (uint32_t)__cvta_generic_to_shared(P), Gs = (uint32_t)__cvta_generic_to_shared(G);
+                uint32_t wps = (uint32_t)__cvta_generic_to_shared(wp);
+                asm volatile("" : "+r"(Ps), "+r"(Gs), "+r"(wps));
                 const uint32_t PS2 = (uint32_t)PS * 2u, RHPS2 = (uint32_t)RH * PS2;
                 if (LOGN) {
                     // per-grain radii: one sample at a time, per cell row FG_TILE_USLOTS predicated tests
@@ -716,7 +720,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                     // the arithmetic), which doubles the independent work in flight per warp.
 #pragma unroll
                     for (int s = 0; s < SPWC; s += 2) {
-                        const float2 pdA = wp[yl * SPWC + s], pdB = wp[yl * SPWC + s + 1];
+                        const float2 pdA = lds_f32x2(wps + (uint32_t)(yl * SPWC + s) * 8u), pdB = lds_f32x2(wps + (uint32_t)(yl * SPWC + s + 1) * 8u);
                         const uint32_t jpA = __float_as_uint(pdA.y), jpB = __float_as_uint(pdB.y);
                         const uint32_t a2A = ip_r[s] & 0xFFFFu, b2A = ip_r[s] >> 16;
                         const uint32_t a2B = ip_r[s + 1] & 0xFFFFu, b2B = ip_r[s + 1] >> 16;
@@ -1022,6 +1026,7 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     TileRef* d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
     cudaStream_t s = ctx->stream;
     FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[6], s)); // ev[6]..ev[4]: thresholds, bitmap, cell table
     const unsigned tb = (unsigned)std::min<size_t>((n_in + 255) / 256, (size_t)ctx->sm_count * 16);
     k_thresholds<<<tb, 256, 0, s>>>(d_lambda, n_in, p->delta, d_thr, d_e);
     FG_CUDA(ctx, cudaGetLastError());

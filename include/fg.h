@@ -99,6 +99,8 @@ typedef struct fg_stats {
     uint64_t h2d_bytes, d2h_bytes;
     float strip_ms;           /* pixel-wise tiled path: device time of the (last) strip-kernel launch */
     uint32_t strip_launches;  /*   strip-kernel launches of the call (row sub-bands; normally 1) */
+    float table_ms;           /*   device time of the (last) band's thresholds + bitmap + cell-table kernels */
+    uint32_t reserved;
 } fg_stats;
 
 int fg_abi_version(void);
