@@ -14,7 +14,13 @@
 
 namespace fg {
 
-__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+// 64-bit rotate as two 32-bit funnel shifts (k is a compile-time constant at every call site)
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    if (k & 32) { const uint32_t t = lo; lo = hi; hi = t; }
+    const uint32_t nhi = __funnelshift_l(lo, hi, k & 31), nlo = __funnelshift_l(hi, lo, k & 31);
+    return ((uint64_t)nhi << 32) | nlo;
+}
 
 // src/rng.rs:46-52
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

@@ -856,6 +856,69 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
     }
 }
 
+// Fallback of the STAGED strip kernel: strip segments whose window does not fit the shared-memory
+// rings (dense content: more grains per window than the grain ring holds) are evaluated straight from
+// the HBM cell table -- the same candidate ranges, read through L2 instead of shared memory -- rather
+// than by regenerating every cell per sample.  Work item = one 32 x 8 pixel chunk of one listed tile.
+// A sample whose cells leave the table rectangle (cannot happen for planned geometry) takes the
+// regenerating indicator.
+template <bool LOGN>
+__global__ void __launch_bounds__(256) k_pixelwise_table_tiles(const float* __restrict__ lambda, size_t lambda_stride,
+                                                                const float2* __restrict__ offsets_input,
+                                                                float* __restrict__ out, size_t out_stride,
+                                                                const TileRef* __restrict__ tiles,
+                                                                const uint32_t* __restrict__ n_tiles, uint32_t tile_cap,
+                                                                uint32_t chunks_per_tile, uint32_t* __restrict__ n_total,
+                                                                TileCfg cfg, RenderConsts c, CellTable tab) {
+    const uint32_t nt = min(*n_tiles, tile_cap);
+    if (n_total && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_total, nt);
+    const uint64_t work = (uint64_t)nt * chunks_per_tile;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float rm = c.rad.rm, delta = c.delta, r2c = cfg.r2c;
+    const bool radius_ok = LOGN || r2c > 0.0f;
+    for (uint64_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
+        const TileRef t = tiles[wi / chunks_per_tile];
+        const int yl = (int)(wi % chunks_per_tile) * 8 + ty;
+        if (yl >= t.h || tx >= t.w) continue;
+        const int x = t.x0 + tx, y = t.y0 + yl;
+        if (x >= c.out_w || y >= c.row_end) continue;
+        const float* lam = lambda + lambda_stride * t.plane;
+        const size_t prow0 = (size_t)t.plane * cfg.bm_rows;
+        const float bx = __fmul_rn(__fadd_rn((float)x, 0.5f), c.inv_zoom);
+        const float by = __fmul_rn(__fadd_rn((float)y, 0.5f), c.inv_zoom);
+        uint32_t count = 0;
+        for (uint32_t k = 0; k < c.n; ++k) {
+            const float2 o = __ldg(offsets_input + k);
+            const float xg = __fsub_rn(bx, o.x), yg = __fsub_rn(by, o.y);
+            if (!(rm > 0.0f)) continue;
+            const int i0 = cell_lo(xg, rm, delta), i1 = cell_hi(xg, rm, delta);
+            const int j0 = cell_lo(yg, rm, delta), j1 = cell_hi(yg, rm, delta);
+            if (i0 > i1 || j0 > j1) continue;
+            if (i0 < cfg.bm_i0 || (long long)i1 >= (long long)cfg.bm_i0 + cfg.bm_cols || j0 < cfg.bm_j0 ||
+                (long long)j1 >= (long long)cfg.bm_j0 + cfg.bm_rows) {
+                count += indicator_direct(lam, c, xg, yg) ? 1u : 0u;
+                continue;
+            }
+            if (!radius_ok) continue;
+            bool hit = false;
+            for (int j = j0; j <= j1 && !hit; ++j) {
+                const size_t row = prow0 + (size_t)(j - cfg.bm_j0);
+                const uint32_t* pr = tab.Pg + row * cfg.ppitch + (uint32_t)(i0 - cfg.bm_i0);
+                const uint32_t s = __ldg(pr), e = __ldg(pr + (i1 - i0 + 1));
+                const size_t base = (size_t)__ldg(tab.rowbase + row);
+                for (uint32_t g = s; g < e; ++g) {
+                    const float2 gr = __ldg(tab.Gg + base + g);
+                    const float rr2 = LOGN ? __ldg(tab.R2g + base + g) : r2c; // LOGN: -1 = radius <= 0, never covers
+                    const float dx = __fsub_rn(xg, gr.x), dy = __fsub_rn(yg, gr.y);
+                    if (__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= rr2) { hit = true; break; }
+                }
+            }
+            count += hit ? 1u : 0u;
+        }
+        out[out_stride * t.plane + (size_t)y * c.out_w + x] = __fmul_rn((float)count, c.inv_samples);
+    }
+}
+
 } // namespace fg
 
 namespace {
@@ -1102,8 +1165,15 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
     const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);
     const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units * chunks, (uint64_t)ctx->sm_count * 8);
-    k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
-                                                 chunks, d_fbtotal, c);
+    if (staged && c.rad.lognorm)
+        k_pixelwise_table_tiles<true><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
+                                                          chunks, d_fbtotal, g, c, tab);
+    else if (staged)
+        k_pixelwise_table_tiles<false><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
+                                                           chunks, d_fbtotal, g, c, tab);
+    else
+        k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
+                                                     chunks, d_fbtotal, c);
     FG_CUDA(ctx, cudaGetLastError());
     ctx->stats.launches += 2;
     if (std::getenv("FG_B200_DEBUG"))

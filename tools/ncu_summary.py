@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an ncu report (run here, no GPU needed): key raw metrics + instructions per source line.
 
-usage: python tools/ncu_summary.py gpurun_out/foo.ncu-rep [--top 30] > profiles/foo_summary.txt
+usage: python tools/ncu_summary.py gpurun_out/foo.ncu-rep [--top 30] [--kernel REGEX] > profiles/foo_summary.txt
 """
 import csv
 import io
@@ -20,6 +20,9 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.
 
 
 def run(args):
+    # --kernel <regex> (optional) selects one kernel of a multi-kernel report
+    if "--kernel" in sys.argv:
+        args = args + ["-k", "regex:" + sys.argv[sys.argv.index("--kernel") + 1]]
     return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
 
 
