@@ -298,6 +298,7 @@ int fg_context_create(fg_ctx** out, int device) {
             const unsigned long long b = std::strtoull(v, nullptr, 10);
             if (b >= (1ULL << 20)) ctx->table_max = (size_t)b;
         }
+        if (const char* v = std::getenv("FG_B200_TABLE_SLACK_SIGMA")) ctx->table_slack_sigma = std::atof(v);
     }
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
         cudaGetLastError();

@@ -39,6 +39,7 @@ struct fg_ctx {
     uint32_t fb_count_host = 0; // tiled path: fallback-list length of the last render (valid after a stream sync)
     bool fb_pending = false;
     size_t table_max = (size_t)48 << 30; // cell-table budget per band (FG_B200_TABLE_MAX_BYTES overrides; tests)
+    double table_slack_sigma = 8.0; // row capacity = expected grains + this many sigma + 64 (FG_B200_TABLE_SLACK_SIGMA: tests)
     uint32_t strip_launches = 0; // strip-kernel launches of the last pixel-wise render (row sub-bands)
 };
 

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) k_row_expect(const float* __restrict__ la
 
 // Row capacities and their exclusive prefix (one CTA of 1024 threads; n = planes * rows is ~1e5).
 // rowbase[n] = total entries; UINT64_MAX if a row is too large for 32-bit in-row prefixes.
-__global__ void __launch_bounds__(1024) k_row_bases(const double* __restrict__ S, int j0, int rows, int n_planes,
+__global__ void __launch_bounds__(1024) k_row_bases(const double* __restrict__ S, int j0, int rows, int n_planes, double slack_sigma,
                                                      uint64_t* __restrict__ rowbase, uint32_t* __restrict__ rowcap, RenderConsts c) {
     __shared__ uint64_t wsum[32];
     __shared__ int bad;
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(1024) k_row_bases(const double* __restrict__ S
         const int pl = r / rows, row = r - pl * rows;
         const int iy = min(max(floor_i32(__fmul_rn(__int2float_rn(j0 + row), c.delta)), 0), c.in_h - 1);
         const double s = S[(size_t)pl * c.in_h + iy];
-        const double cap = s + 8.0 * sqrt(s) + 64.0;
+        const double cap = fmax(s + slack_sigma * sqrt(s), 0.0) + 64.0;
         if (!(cap < 3.0e9)) { bad = 1; return 0u; }
         return (uint32_t)cap;
     };

@@ -1048,8 +1048,9 @@ void launch_strip(int spwc, uint32_t units, uint32_t smem, cudaStream_t s, Args.
 #define FG_TABLE_BYTES_MAX ((size_t)48 << 30)
 #endif
 
-// One band [c.row_begin, c.row_end).  returns FG_OK (rendered), 1 (tiled path not applicable), 2 (staged
-// mode not possible for this band: caller retries with in-kernel generation) or an error.
+// One band [c.row_begin, c.row_end).  returns FG_OK (rendered), 1 (tiled path not applicable), 2 (the
+// cell table of this band does not fit the memory budget: caller splits the band), 3 (the table
+// overflowed: caller uses in-kernel generation) or an error.
 int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
                      const float* d_offsets, float* d_out, bool staged, uint32_t* d_fbtotal) {
     TilePlan pl = tile_plan(ctx, p, c, n_planes, staged);
@@ -1111,14 +1112,17 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         const size_t s_bytes = align_up((uint32_t)((size_t)n_planes * p->in_h * 8), 256);
         const size_t base_bytes = (n_rows_all + 1) * 8, cap_bytes = n_rows_all * 4;
         if ((rc = ensure(ctx, ctx->rowinfo, s_bytes + base_bytes + cap_bytes + 256 + 64))) return rc;
-        if ((rc = ensure(ctx, ctx->ptab, pg_bytes))) return rc;
+        if ((rc = ensure(ctx, ctx->ptab, pg_bytes))) {
+            if (rc == FG_ERR_OOM) { ctx->err.clear(); return 2; }
+            return rc;
+        }
         double* d_S = (double*)ctx->rowinfo.p;
         uint64_t* d_rowbase = (uint64_t*)((unsigned char*)ctx->rowinfo.p + s_bytes);
         uint32_t* d_rowcap = (uint32_t*)((unsigned char*)d_rowbase + (base_bytes + 255) / 256 * 256);
         uint32_t* d_overflow = (uint32_t*)((unsigned char*)d_rowcap + (cap_bytes + 63) / 64 * 64);
         k_row_expect<<<dim3(p->in_h, n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, d_S, c);
         FG_CUDA(ctx, cudaGetLastError());
-        k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, d_rowbase, d_rowcap, c);
+        k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, ctx->table_slack_sigma, d_rowbase, d_rowcap, c);
         FG_CUDA(ctx, cudaGetLastError());
         FG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 4, s));
         uint64_t total = 0;
@@ -1146,7 +1150,7 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));
         FG_CUDA(ctx, cudaStreamSynchronize(s));
         ctx->stats.launches += 3;
-        if (overflow) return 2; // a row outgrew its expected size + 8 sigma: regenerate in-kernel instead
+        if (overflow) return 3; // a row outgrew its expected size + 8 sigma (or a cell holds > 65535 grains): regenerate in-kernel instead
         tab.Pg = (const uint32_t*)ctx->ptab.p;
         tab.rowbase = d_rowbase;
         tab.Gg = d_G;
@@ -1196,25 +1200,23 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
     ctx->strip_launches = 0;
     bool staged = path != FG_PATH_TILED;
     rc = tile_render_band(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, staged, d_fbtotal);
-    if (rc == 2) {
-        // the whole band does not fit one table: split it into row sub-bands, else generate in-kernel
+    if (rc == 2 || rc == 3) {
+        // 2: the whole band does not fit one table -> row sub-bands; whatever cannot be staged (and
+        // 3: a table overflow) is rendered with in-kernel generation
         const int band = c.row_end - c.row_begin;
         int done = c.row_begin;
-        bool ok = true;
-        for (int parts = 2; parts <= 64 && done == c.row_begin; parts *= 2) {
+        for (int parts = 2; rc == 2 && parts <= 64 && done == c.row_begin; parts *= 2) {
             const int rows = (band + parts - 1) / parts;
             if (rows < 64) break;
-            ok = true;
-            for (int y = c.row_begin; y < c.row_end && ok; y += rows) {
+            for (int y = c.row_begin; y < c.row_end; y += rows) {
                 RenderConsts cb = c;
                 cb.row_begin = y;
                 cb.row_end = std::min(y + rows, c.row_end);
-                rc = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, true, d_fbtotal);
-                if (rc == 2 || rc == 1) { ok = false; break; }
-                if (rc) return rc;
+                const int r2 = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, true, d_fbtotal);
+                if (r2 == 1 || r2 == 2 || r2 == 3) break;
+                if (r2) return r2;
                 done = cb.row_end;
             }
-            if (ok) break;
         }
         if (done < c.row_end) { // finish (or redo) the rest with in-kernel generation
             RenderConsts cb = c;

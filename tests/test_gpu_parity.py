@@ -162,6 +162,23 @@ def test_staged_path_splits_into_row_bands_when_the_table_budget_is_small(monkey
     assert np.array_equal(ref, got)
 
 
+def test_staged_path_table_overflow_falls_back_to_in_kernel_generation(monkeypatch):
+    """Row capacities are expected grains + 8 sigma; with the slack forced negative every row
+    overflows, the gen kernel raises its flag and the band is rendered by the in-kernel generator."""
+    w, h = 96, 72
+    p = O.make_params(radius=0.1, n_samples=8, algo=O.ALGO_PIXEL)
+    d, off, off_in = O.derive_common(p, w, h)
+    lam = lambda_from_u8(noise_u8(w, h, seed=4)[:, :, 0], d.inv_e_pi_r2)
+    ref = O.render_pixelwise(lam, p, d, off_in)
+    import film_grain_b200 as fg
+    monkeypatch.setenv("FG_B200_TABLE_SLACK_SIGMA", "-40")
+    with fg.Context(0) as tight:
+        got = tight.render_pixelwise(fg_params_from(p, d, path=3), lam, off_in)
+        st = tight.stats()
+    assert st.strip_launches == 1 and st.tiles_total > 0
+    assert np.array_equal(ref, got)
+
+
 GRAIN_CASES = [
     ("r0.5_N16", 64, 48, dict(radius=0.5, n_samples=16)),
     ("r0.5_N70", 40, 40, dict(radius=0.5, n_samples=70)),
