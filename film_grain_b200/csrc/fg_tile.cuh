@@ -182,6 +182,15 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t addr) {
     return v;
 }
 
+// asynchronous global -> shared copies (LDGSTS): no registers, completion by cp.async.wait_all
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // squared distance with the packed f32x2 pipe: (dx, dy) = p - g and (dx*dx, dy*dy) are one instruction
 // each (FADD2 / FMUL2, round-to-nearest per element like the scalar forms), then dx*dx + dy*dy.
 __device__ __forceinline__ float dist2_packed(uint64_t p, float2 g) {
@@ -233,6 +242,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
     uint32_t* pcount = (uint32_t*)(smem + cfg.off_pcount);
     float2* wpair = (float2*)(smem + cfg.off_wpair);
     uint32_t* rowA = (uint32_t*)(smem + cfg.off_rows); // STAGED: [RH] first table prefix of the window, [RH] count, [RH] ring position
+    uint32_t* extb = rowA + (3 * cfg.RH + 3) / 4 * 4;                // STAGED: [RH][4] prefetched {Pg[first], Pg[last], rowbase lo, hi} of the next step's rows
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -341,6 +351,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
     int j_lo_prev = 0, rr_lo = 0; // oldest live cell row and its ring row
     bool first = true;
     int r_cur = cfg.R;            // rows per generation group (adapts to the non-empty fraction)
+    int pf_j0 = INT_MIN, pf_n = 0; // STAGED: cell rows whose extents were prefetched into extb
 
     for (int ya = Y0; ya < Y1; ya += cfg.TH) {
         const int yb = min(ya + cfg.TH, Y1) - 1; // inclusive
@@ -380,6 +391,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             uint32_t* rowH = rowN + RH;
             const size_t trow0 = (size_t)plane * cfg.bm_rows + (size_t)(j_gen - cfg.bm_j0);
             const uint32_t tcol0 = (uint32_t)(i_lo - cfg.bm_i0);
+            const bool have_pf = (pf_j0 == j_gen && pf_n >= nn); // uniform
             // Every warp computes the placement of ALL new rows itself (same loads, same scan, same
             // verdict) and writes the same values to rowA/rowN/rowH: no CTA barrier, no exchange.
             uint32_t nhead;
@@ -392,9 +404,14 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                 for (int t0 = 0; t0 < nn; t0 += 32) {
                     uint32_t a = 0, v = 0;
                     if (t0 + lane < nn) {
-                        const uint32_t* pr = tab.Pg + (trow0 + t0 + lane) * cfg.ppitch + tcol0;
-                        a = __ldg(pr);
-                        v = __ldg(pr + CW) - a;
+                        if (have_pf) { // fetched into shared memory while the previous step evaluated
+                            a = extb[4 * (t0 + lane)];
+                            v = extb[4 * (t0 + lane) + 1] - a;
+                        } else {
+                            const uint32_t* pr = tab.Pg + (trow0 + t0 + lane) * cfg.ppitch + tcol0;
+                            a = __ldg(pr);
+                            v = __ldg(pr + CW) - a;
+                        }
                     }
                     uint32_t incl = v;
 #pragma unroll
@@ -432,7 +449,13 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                 int rr = rr_gen + t;
                 if (rr >= RH) rr -= RH;
                 const uint4* pr4 = (const uint4*)(tab.Pg + (trow0 + t) * cfg.ppitch + (tcol0 - (uint32_t)sh));
-                const size_t gsrc = (size_t)__ldg(tab.rowbase + trow0 + t) + a;
+                const size_t gsrc = (have_pf ? (size_t)(((uint64_t)extb[4 * t + 3] << 32) | extb[4 * t + 2]) : (size_t)__ldg(tab.rowbase + trow0 + t)) + a;
+                // the row's grain slice goes straight to the ring, asynchronously, while the prefix row is
+                // loaded and converted below
+                for (uint32_t kk = lane; kk < n; kk += 32) {
+                    cp_async8(G + h + kk, tab.Gg + gsrc + kk);
+                    if (LOGN) cp_async4(R2 + h + kk, tab.R2g + gsrc + kk);
+                }
                 uint2* prow = (uint2*)(P + rr * PS);
                 uint2* pmir = (uint2*)(P + (rr + RH) * PS); // rows 0 and 1 again behind row RH - 1
                 const int n4 = (CW1 + sh + 3) >> 2;
@@ -457,27 +480,8 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                         }
                     }
                 }
-                for (uint32_t k0 = 0; k0 < n; k0 += 128) {
-                    float2 gv[4];
-                    float rv[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t kk = k0 + 32 * k + lane;
-                        if (kk < n) {
-                            gv[k] = __ldg(tab.Gg + gsrc + kk);
-                            if (LOGN) rv[k] = __ldg(tab.R2g + gsrc + kk);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint32_t kk = k0 + 32 * k + lane;
-                        if (kk < n) {
-                            G[h + kk] = gv[k];
-                            if (LOGN) R2[h + kk] = rv[k];
-                        }
-                    }
-                }
             }
+            cp_async_wait_all();
             head = nhead;
             j_gen += nn;
             rr_gen += nn;
@@ -638,6 +642,32 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             // no barrier here: the next group only touches cntA/list/E behind its own barriers
         }
         __syncthreads(); // P and G complete before the evaluation reads them
+
+        // STAGED: while this step evaluates, fetch what the next step's placement needs (first/last
+        // prefix of each new row's window slice and the row's base) into shared memory
+        if (STAGED) {
+            pf_n = 0;
+            const int ya2 = ya + cfg.TH;
+            if (ya2 < Y1) {
+                const int yb2 = min(ya2 + cfg.TH, Y1) - 1;
+                const float bya2 = __fmul_rn(__fadd_rn((float)ya2, 0.5f), c.inv_zoom);
+                const float byb2 = __fmul_rn(__fadd_rn((float)yb2, 0.5f), c.inv_zoom);
+                const int j_lo2 = cell_lo(__fsub_rn(bya2, c.off_max_y), rm, delta);
+                const int j_hi2 = cell_hi(__fsub_rn(byb2, c.off_min_y), rm, delta);
+                const long long nn2 = (long long)j_hi2 - j_gen + 1;
+                if (j_lo2 <= j_gen && nn2 > 0 && nn2 <= RH && (long long)j_hi2 < (long long)cfg.bm_j0 + cfg.bm_rows) {
+                    pf_j0 = j_gen;
+                    pf_n = (int)nn2;
+                    const size_t trow2 = (size_t)plane * cfg.bm_rows + (size_t)(j_gen - cfg.bm_j0);
+                    for (int t = tid; t < pf_n; t += FG_TILE_THREADS) {
+                        const uint32_t* pr = tab.Pg + (trow2 + t) * cfg.ppitch + (uint32_t)(i_lo - cfg.bm_i0);
+                        cp_async4(extb + 4 * t, pr);
+                        cp_async4(extb + 4 * t + 1, pr + CW);
+                        cp_async8(extb + 4 * t + 2, tab.rowbase + trow2 + t);
+                    }
+                }
+            }
+        }
 
         // =================== evaluation of pixel rows ya..yb ===================
         for (int chunk = 0; chunk < n_chunks; ++chunk) {
@@ -844,6 +874,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             }
             __syncwarp();
         }
+        if (STAGED) cp_async_wait_all(); // the extents prefetched above (visible to all after the barrier)
         __syncthreads();
         for (int p = tid; p < th * 32; p += FG_TILE_THREADS) {
             const int yl = p >> 5, xl = p & 31;
@@ -967,7 +998,7 @@ TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
             g.off_list = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
             g.off_E = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
             g.off_cnt = off; off = align_up(off + (staged ? 0u : (uint32_t)(FG_TILE_NE + 8) * 4u), 16);
-            g.off_rows = off; off = align_up(off + (staged ? (uint32_t)RH * 12u : 0u), 16);
+            g.off_rows = off; off = align_up(off + (staged ? (uint32_t)RH * 28u + 16u : 0u), 16);
             g.off_wtot = off; off = align_up(off + (uint32_t)(FG_TILE_WARPS + 4) * 4u, 16);
             g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
             g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
