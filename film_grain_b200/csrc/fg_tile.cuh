@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ la
 // one thread per cell column; each warp
 // stores one aligned 32-bit word per plane.
 #define FG_BM_ROWS 16 // cell rows per thread in k_first_draw_bitmap (amortises the column half of the hash)
-template <int SEEDING> // compile-time: a run-time select gets if-converted and issues both seeders
+template <int SEEDING, int NP> // compile-time seeding variant and plane count (NP = 0: run-time n_planes)
 __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __restrict__ thr_planes, size_t in_stride,
                                                             int n_planes, uint32_t* __restrict__ bm, size_t bm_plane_words,
                                                             int i0, int j0, int cols, int rows, uint32_t pitchw, RenderConsts c) {
@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __res
             const int iy = min(max(floor_i32(__fmul_rn(__int2float_rn(j), c.delta)), 0), c.in_h - 1);
             pix = (size_t)iy * c.in_w + ix;
         }
-        for (int pl = 0; pl < n_planes; ++pl) {
+        const int np = NP ? NP : n_planes;
+#pragma unroll
+        for (int pl = 0; pl < np; ++pl) {
             bool ne = false;
             if (valid) {
                 const uint64_t th64 = __ldg(thr_planes + in_stride * pl + pix);
@@ -1128,12 +1130,17 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
     {
         dim3 bgrid((unsigned)((g.bm_rows + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
-        if (c.seeding == 0)
-            k_first_draw_bitmap<0><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, g.bm_cols,
-                                                         g.bm_rows, g.bm_pitchw, c);
-        else
-            k_first_draw_bitmap<1><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, g.bm_cols,
-                                                         g.bm_rows, g.bm_pitchw, c);
+#define FG_LAUNCH_BM(SD, NPL)                                                                                       \
+    k_first_draw_bitmap<SD, NPL><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, \
+                                                       g.bm_cols, g.bm_rows, g.bm_pitchw, c)
+        if (c.seeding == 0) {
+            if (n_planes == 3) FG_LAUNCH_BM(0, 3);
+            else if (n_planes == 1) FG_LAUNCH_BM(0, 1);
+            else FG_LAUNCH_BM(0, 0);
+        } else {
+            FG_LAUNCH_BM(1, 0);
+        }
+#undef FG_LAUNCH_BM
         FG_CUDA(ctx, cudaGetLastError());
     }
     ctx->stats.launches += 2;
