@@ -395,7 +395,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
             const uint32_t tcol0 = (uint32_t)(i_lo - cfg.bm_i0);
             const bool have_pf = (pf_j0 == j_gen && pf_n >= nn); // uniform
             // Every warp computes the placement of ALL new rows itself (same loads, same scan, same
-            // verdict) and writes the same values to rowA/rowN/rowH: no CTA barrier, no exchange.
+            // verdict) and keeps the entries of the rows it copies: no CTA barrier, no exchange.
             uint32_t nhead;
             {
                 const bool live = j_lo < j_gen;             // rows of earlier steps still in the window
@@ -435,7 +435,8 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                     } else {
                         cur += tot;
                     }
-                    if (t0 + lane < nn) { rowA[t0 + lane] = a; rowN[t0 + lane] = v; rowH[t0 + lane] = pos; }
+                    // a row's entry has one writer: the warp that copies that row below
+                    if (t0 + lane < nn && (t0 + lane) % FG_TILE_WARPS == warp) { rowA[t0 + lane] = a; rowN[t0 + lane] = v; rowH[t0 + lane] = pos; }
                 }
                 // the new rows must end strictly before the oldest live grain
                 if ((wrapped || wrapped0) && cur >= tail) bad = true;
