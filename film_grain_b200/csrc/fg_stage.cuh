@@ -22,8 +22,8 @@ namespace fg {
 // Expected grains of one cell row, per (plane, input row): sum over the band's cell columns of
 // lambda' = lambda * delta^2 (src/pixelwise.rs:76-81) at the clamped input pixel of the column.
 __global__ void __launch_bounds__(256) k_row_expect(const float* __restrict__ lambda, size_t in_stride, int i0, int cols,
-                                                     double* __restrict__ S, RenderConsts c) {
-    const int iy = blockIdx.x, pl = blockIdx.y;
+                                                     int iy_first, double* __restrict__ S, RenderConsts c) {
+    const int iy = iy_first + blockIdx.x, pl = blockIdx.y; // only the input rows the band's cell rows map to
     const float* lrow = lambda + in_stride * pl + (size_t)iy * c.in_w;
     double s = 0.0;
     for (int col = threadIdx.x; col < cols; col += 256) {

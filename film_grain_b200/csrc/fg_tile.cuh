@@ -38,10 +38,12 @@ namespace fg {
 // Per input pixel: thr = floor(exp(-lambda') * 2^53), e = exp(-lambda') with lambda' = lambda*delta*delta
 // (src/pixelwise.rs:71-81).  The Knuth loop's first decision `p = U1 > e` with U1 = m * 2^-53
 // (m = next_u64 >> 11) is exactly `m > thr`.
-__global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ lambda, size_t n, float delta,
-                                                     uint64_t* __restrict__ thr, double* __restrict__ ev) {
+__global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ lambda, size_t in_stride, size_t first, size_t n,
+                                                     float delta, uint64_t* __restrict__ thr, double* __restrict__ ev) {
+    // blockIdx.y = plane; elements [first, first + n) of each plane (the input rows the band's cells map to)
+    const size_t base = in_stride * blockIdx.y + first;
     for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (size_t)gridDim.x * 256) {
-        float lam = lambda[t];
+        float lam = lambda[base + t];
         uint64_t th = FG_THR_EMPTY;
         double e = 1.0;
         if (lam > 0.0f) {
@@ -59,8 +61,8 @@ __global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ la
             th = FG_THR_GENERAL;
             e = -1.0;
         }
-        thr[t] = th;
-        ev[t] = e;
+        thr[base + t] = th;
+        ev[base + t] = e;
     }
 }
 
@@ -1125,8 +1127,12 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     cudaStream_t s = ctx->stream;
     FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[6], s)); // ev[6]..ev[4]: thresholds, bitmap, cell table
-    const unsigned tb = (unsigned)std::min<size_t>((n_in + 255) / 256, (size_t)ctx->sm_count * 16);
-    k_thresholds<<<tb, 256, 0, s>>>(d_lambda, n_in, p->delta, d_thr, d_e);
+    // input rows the band's cell rows map to (clamped like Plane::get_clamped), one row of slack
+    const int iy0 = std::min(std::max((int)std::floor((double)g.bm_j0 * (double)p->delta) - 1, 0), (int)p->in_h - 1);
+    const int iy1 = std::min(std::max((int)std::floor((double)(g.bm_j0 + g.bm_rows) * (double)p->delta) + 1, 0), (int)p->in_h - 1);
+    const size_t thr_first = (size_t)iy0 * p->in_w, thr_n = (size_t)(iy1 - iy0 + 1) * p->in_w;
+    const unsigned tb = (unsigned)std::min<size_t>((thr_n + 255) / 256, (size_t)ctx->sm_count * 16);
+    k_thresholds<<<dim3(tb, (unsigned)n_planes), 256, 0, s>>>(d_lambda, in_stride, thr_first, thr_n, p->delta, d_thr, d_e);
     FG_CUDA(ctx, cudaGetLastError());
     uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
     {
@@ -1159,7 +1165,7 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         uint64_t* d_rowbase = (uint64_t*)((unsigned char*)ctx->rowinfo.p + s_bytes);
         uint32_t* d_rowcap = (uint32_t*)((unsigned char*)d_rowbase + (base_bytes + 255) / 256 * 256);
         uint32_t* d_overflow = (uint32_t*)((unsigned char*)d_rowcap + (cap_bytes + 63) / 64 * 64);
-        k_row_expect<<<dim3(p->in_h, n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, d_S, c);
+        k_row_expect<<<dim3((unsigned)(iy1 - iy0 + 1), n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, iy0, d_S, c);
         FG_CUDA(ctx, cudaGetLastError());
         k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, ctx->table_slack_sigma, d_rowbase, d_rowcap, c);
         FG_CUDA(ctx, cudaGetLastError());
