@@ -24,10 +24,15 @@ def max_band_rows(out_h: int, world: int) -> int:
     return (out_h + world - 1) // world
 
 
+_gather_cache: dict = {}
+
+
 def gather_bands(band, out_h: int, rank: int, world: int, dst: int = 0, group=None):
     """Gather per-rank bands [..., rows_r, W(, C)] (row axis = -2 for planes [P,rows,W]; pass tensors whose
     dim 0 is the row axis) to `dst`.  Bands are padded to the common maximum so one collective moves
-    everything; returns the assembled [out_h, ...] tensor on dst, None elsewhere."""
+    everything; returns the assembled [out_h, ...] tensor on dst, None elsewhere.  The receive buffer is
+    allocated once per shape and reused (the returned tensor is overwritten by the next call); when the
+    rows divide evenly the bands land directly in place, otherwise they are compacted with one copy."""
     import torch
     import torch.distributed as dist
 
@@ -40,8 +45,16 @@ def gather_bands(band, out_h: int, rank: int, world: int, dst: int = 0, group=No
         band = torch.cat([band, pad], dim=0)
     band = band.contiguous()
     if rank == dst:
-        parts = [torch.empty_like(band) for _ in range(world)]
+        key = (tuple(band.shape), band.dtype, band.device, world)
+        recv = _gather_cache.get(key)
+        if recv is None:
+            recv = torch.empty((world * mx,) + tuple(band.shape[1:]), dtype=band.dtype, device=band.device)
+            _gather_cache.clear()
+            _gather_cache[key] = recv
+        parts = [recv[r * mx:(r + 1) * mx] for r in range(world)]
         dist.gather(band, parts, dst=dst, group=group)
+        if out_h == world * mx:
+            return recv
         pieces = []
         for r in range(world):
             b, e = band_rows(out_h, r, world)
