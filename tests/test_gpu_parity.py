@@ -144,6 +144,27 @@ def test_tiled_path_is_taken_and_fallback_is_exact(ctx, path):
     assert np.array_equal(got3, O.render_pixelwise(lam3, p3, d3, off_in3))
 
 
+@pytest.mark.parametrize("dist", ["const", "lognorm"])
+def test_staged_fallback_reads_the_cell_table(ctx, dist):
+    """Saturated content overflows the strip kernel's grain ring; in staged mode those segments are
+    evaluated straight from the HBM cell table (k_pixelwise_table_tiles, both radius models) and must
+    equal the oracle and the regenerating direct kernel bit for bit."""
+    w, h = 128, 96
+    kw = dict(radius=0.1, n_samples=12, algo=O.ALGO_PIXEL)
+    if dist == "lognorm":
+        kw.update(radius_dist=O.DIST_LOGNORM, radius_stddev=0.05)
+    p = O.make_params(**kw)
+    d, off, off_in = O.derive_common(p, w, h)
+    img = noise_u8(w, h, seed=21)
+    img[30:, 40:, :] = 255
+    lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
+    got = ctx.render_pixelwise(fg_params_from(p, d, path=3), lam, off_in)
+    st = ctx.stats()
+    assert 0 < st.tiles_fallback <= st.tiles_total, (st.tiles_total, st.tiles_fallback)
+    assert np.array_equal(got, O.render_pixelwise(lam, p, d, off_in))
+    assert np.array_equal(got, ctx.render_pixelwise(fg_params_from(p, d, path=1), lam, off_in))
+
+
 def test_staged_path_splits_into_row_bands_when_the_table_budget_is_small(monkeypatch):
     """A render whose cell table exceeds the budget is split into row sub-bands (each with its own
     table); the result and the fallback accounting do not change."""
