@@ -9,8 +9,11 @@ on BASELINE.json configs[1]: pixel-wise RGB 3840x2160 synthetic noise, radius 0.
 A "step" is one full render of the image (3 colour planes).
 
   value : inputs (lambda planes, offsets) resident in HBM; device time (CUDA events on the engine's
-          stream) from the first kernel to the finished image resident on GPU 0 (bands gathered with
-          NCCL for N > 1); max over ranks.
+          stream) from the first kernel to the finished image resident on GPU 0; max over ranks.
+          N > 1: every rank's kernels store their band rows straight into GPU 0's image over NVLink
+          (peer-mapped buffer, one device-side barrier ends the step; film_grain_b200/dist.py
+          PeerImage), or -- where peer mapping cannot be set up, or with --bands gather -- the bands
+          are gathered with NCCL.
   e2e   : the same render through the reference-facing C-ABI call with HOST buffers
           (fg_render_planes: f32 lambda planes in, f32 planes out; copies inside the timed region).
   roofline : ALU-issue roofline (the path is integer/FP32-ALU bound, not HBM- or tensor-bound):
@@ -208,6 +211,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--bands", default="auto", choices=["auto", "peer", "gather"],
+                    help="N > 1: how the finished bands reach GPU 0 (peer = the kernels store straight into GPU 0's image "
+                         "over NVLink; gather = NCCL gather; auto = peer when it can be set up)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -224,13 +230,14 @@ def main():
 
     import film_grain_b200 as fg
     from film_grain_b200 import host as H
-    from film_grain_b200.dist import band_rows, gather_bands
+    from film_grain_b200.dist import PeerImage, band_rows, gather_bands
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
@@ -255,9 +262,21 @@ def main():
     d_off = torch.from_numpy(np.ascontiguousarray(offsets)).to(dev)
     d_out = torch.zeros((planes, out_h, out_w), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # N > 1: GPU 0's image mapped into every rank (NVLink peer stores), else the NCCL gather below
+    peer = None
+    if world > 1 and args.bands != "gather":
+        peer = PeerImage.create((planes, out_h, out_w), torch.float32, dev, rank, world)
+        if peer is None and args.bands == "peer":
+            raise SystemExit("--bands peer: the peer image could not be set up on every rank")
     torch.cuda.synchronize()
 
     def step_device():
+        if peer is not None:
+            # every rank's kernels write their band rows straight into GPU 0's image; one device-side
+            # barrier on the engine's stream ends the step
+            ctx.render_planes_device(blk, algo, planes, d_lam.data_ptr(), d_off.data_ptr(), peer.target.data_ptr(), sync=False)
+            peer.finish()
+            return peer.local if rank == 0 else None
         ctx.render_planes_device(blk, algo, planes, d_lam.data_ptr(), d_off.data_ptr(), d_out.data_ptr(), sync=False)
         if world > 1:  # finished image resident on GPU 0: gather the row bands (NCCL over NVLink)
             band = d_out[:, rb:re, :].permute(1, 0, 2).contiguous()
@@ -344,9 +363,12 @@ def main():
         in_r0 = max(0, int(np.floor(rb / wl["zoom"] - reach)))
         in_r1 = min(wl["h"], int(np.ceil(re / wl["zoom"] + reach)) + 1)
         pin_in = torch.from_numpy(np.stack(lam_host)[:, in_r0:in_r1, :].copy()).pin_memory()
-        pin_out = torch.empty((out_h, planes, out_w), dtype=torch.float32).pin_memory() if rank == 0 else None
+        pin_shape = (planes, out_h, out_w) if peer is not None else (out_h, planes, out_w)
+        pin_out = torch.empty(pin_shape, dtype=torch.float32).pin_memory() if rank == 0 else None
         with torch.cuda.stream(stream):
             def step_e2e():
+                if peer is not None:
+                    peer.finish()  # GPU 0 has read the previous image out before anyone overwrites it
                 d_lam[:, in_r0:in_r1, :].copy_(pin_in, non_blocking=True)
                 full = step_device()
                 if rank == 0:
@@ -366,7 +388,8 @@ def main():
         e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
                "h2d_bytes_per_step": int(pin_in.numel() * 4), "d2h_bytes_per_step": int(planes * out_w * out_h * 4),
                "ms_per_step": e2e_ms,
-               "call": "per rank: pinned H2D of the lambda rows its band sees + band render + NCCL band gather; rank 0: D2H of the image"}
+               "call": "per rank: pinned H2D of the lambda rows its band sees + band render + "
+                       + ("peer stores into GPU 0's image + barrier" if peer is not None else "NCCL band gather") + "; rank 0: D2H of the image"}
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -422,6 +445,8 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "seed": 5489, "sigma_px": 0.8, "algo": wl["algo"],
                        "parallelism": f"row-bands x{world}" if world > 1 else "single GPU",
+                       "bands": (None if world == 1 else (f"NVLink peer stores into GPU 0's image ({peer.mode}) + device barrier"
+                                                          if peer is not None else "NCCL gather to GPU 0")),
                        "l2": "flushed between timed iterations (256 MiB memset outside the events)",
                        "tiles": tiles_total, "tiles_fallback": tiles_fb},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

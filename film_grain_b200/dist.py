@@ -62,3 +62,62 @@ def gather_bands(band, out_h: int, rank: int, world: int, dst: int = 0, group=No
         return torch.cat(pieces, dim=0)
     dist.gather(band, None, dst=dst, group=group)
     return None
+
+
+class PeerImage:
+    """The finished image on `dst`, mapped into every rank's address space over NVLink / NVSwitch.
+
+    Bands are independent, so the only inter-GPU step of the path is "the finished bands end up on
+    GPU `dst`".  Instead of rendering into a local buffer and gathering afterwards, every rank hands
+    the engine a pointer INTO `dst`'s image: the kernels' own coalesced stores of the band rows travel
+    over NVLink as peer writes while the band is being computed, and the step ends with one
+    device-side barrier on the engine's stream.  There is no staging copy and no collective.
+
+    The mapping is torch symmetric memory (cuMem allocations whose handles torch exchanges between the
+    ranks; the barrier runs through its signal pads).  `PeerImage.create` returns None when it cannot
+    be set up on every rank (the caller then uses `gather_bands`).
+    """
+
+    def __init__(self, mode, local, target, finish, keep):
+        self.mode, self.local, self.target, self._finish, self._keep = mode, local, target, finish, keep
+
+    def finish(self):
+        """Barrier on the current CUDA stream: after it, every rank's band is complete in `dst`'s image."""
+        self._finish()
+
+    @staticmethod
+    def _agree(ok: bool, device, group) -> bool:
+        import torch
+        import torch.distributed as dist
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return bool(int(flag.item()))
+
+    @classmethod
+    def create(cls, shape, dtype, device, rank: int, world: int, dst: int = 0, group=None, modes=("symm",)):
+        import torch
+        import torch.distributed as dist
+
+        if world == 1:
+            return None
+        shape = tuple(int(s) for s in shape)
+        for mode in modes:
+            made, err = None, None
+            try:
+                if mode == "symm":
+                    import torch.distributed._symmetric_memory as symm
+                    local = symm.empty(shape, dtype=dtype, device=device)
+                    hdl = symm.rendezvous(local, group if group is not None else dist.group.WORLD)
+                    target = local if rank == dst else hdl.get_buffer(dst, shape, dtype)
+                    made = cls(mode, local, target, hdl.barrier, (hdl,))
+                else:
+                    raise ValueError(f"unknown peer image mode {mode!r}")
+            except Exception as e:  # set-up only: a mode that cannot be established is skipped on ALL ranks
+                err = e
+            if cls._agree(made is not None, device, group):
+                return made
+            del made
+            if err is not None and rank == dst:
+                import sys
+                print(f"[film_grain_b200.dist] peer image mode {mode!r} unavailable: {err!r}", file=sys.stderr)
+        return None
