@@ -177,8 +177,12 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
             uint64_t want_blocks = (total + 255) / 256;
             const uint64_t max_blocks = (uint64_t)ctx->sm_count * 64;
             unsigned sblocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-            k_gw_splat<<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
-                                                         (uint32_t*)ctx->bits.p, lanes32, c);
+            if ((size_t)p->out_w * p->out_h * lanes32 < ((size_t)1 << 32)) // word indices relative to row 0 fit 32 bits
+                k_gw_splat<uint32_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
+                                                                       (uint32_t*)ctx->bits.p, lanes32, c);
+            else
+                k_gw_splat<size_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
+                                                                     (uint32_t*)ctx->bits.p, lanes32, c);
             FG_CUDA(ctx, cudaGetLastError());
             ctx->stats.launches += 2;
         }

@@ -203,49 +203,76 @@ __global__ void __launch_bounds__(256) k_gw_fill(const float* __restrict__ lambd
     }
 }
 
-// bounds() of src/grainwise.rs:126-142 with the clip range [lo_lim, hi_lim] (= [0, limit-1],
-// or the row band for y).  Returns false when empty.
-__device__ __forceinline__ bool gw_bounds(float center, float radius, int limit, int lo_lim, int hi_lim, int& lo, int& hi) {
-    int mn = __float2int_ru(__fsub_rn(__fsub_rn(center, radius), 0.5f));
-    int mx = __float2int_rd(__fsub_rn(__fadd_rn(center, radius), 0.5f));
-    if (mx < mn) return false;
-    int last = limit - 1;
-    if (mn > last || mx < 0) return false;
-    mn = max(mn, lo_lim);
-    mx = min(mx, hi_lim);
-    if (mn > mx) return false;
-    lo = mn; hi = mx;
-    return true;
+// bounds() of src/grainwise.rs:126-142 without branches: [ceil((c-r)-0.5), floor((c+r)-0.5)] clipped to
+// [lo_lim, hi_lim]; the range is empty iff lo > hi afterwards (covers "max < min", "min > last" and
+// "max < 0": clipping one end only never turns an empty or outside range into a non-empty one).
+__device__ __forceinline__ void gw_bounds_clip(float center, float radius, int lo_lim, int hi_lim, int& lo, int& hi) {
+    lo = max(__float2int_ru(__fsub_rn(__fsub_rn(center, radius), 0.5f)), lo_lim);
+    hi = min(__float2int_rd(__fsub_rn(__fadd_rn(center, radius), 0.5f)), hi_lim);
 }
 
 // One thread per grain, looping over the N sample offsets (warp-uniform loads of offsets[k]):
 // rasterise the zoomed disk at centre+offset[k] and OR bit k into the per-pixel coverage mask
 // (src/grainwise.rs:66-101).  Lanes of a warp hold consecutive grains of the same input pixels, so
-// their atomics land on neighbouring mask words.
+// their atomics land on neighbouring mask words.  Boxes of at most 2 x 2 pixels (every disk of
+// diameter <= 1 output pixel, i.e. r * zoom <= 0.5) take a straight-line path: four predicated
+// tests and reductions, no loops and no divergent branches; larger boxes take the general loops.
+// The reference's per-row reject `dy_sq > radius_sq` is implied by the pixel test (dx*dx >= 0 and
+// round-to-nearest addition is monotone), so the straight-line path omits it.
+// IDX = uint32_t when the mask has fewer than 2^31 words, else size_t.
+#define FG_GW_OFF_CHUNK 2048 // sample offsets staged in shared memory per pass (16 KB)
+template <typename IDX>
 __global__ void __launch_bounds__(256) k_gw_splat(const GrainRec* __restrict__ grains, const uint64_t* __restrict__ n_grains_ptr,
                                                    const float2* __restrict__ offsets, uint32_t* __restrict__ bits,
                                                    uint32_t lanes32, RenderConsts c) {
+    __shared__ float2 s_off[FG_GW_OFF_CHUNK];
     const uint64_t total = *n_grains_ptr;
     const int last_x = c.out_w - 1, lo_y = c.row_begin, hi_y = c.row_end - 1;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
-        const GrainRec rec = grains[g];
-        if (!(rec.radius_out > 0.0f)) continue;
-        for (uint32_t k = 0; k < c.n; ++k) {
-            const float2 o = __ldg(offsets + k);
-            const float tx = __fadd_rn(rec.cxz, o.x), ty = __fadd_rn(rec.cyz, o.y);
-            int x_min, x_max, y_min, y_max;
-            if (!gw_bounds(tx, rec.radius_out, c.out_w, 0, last_x, x_min, x_max)) continue;
-            if (!gw_bounds(ty, rec.radius_out, c.out_h, lo_y, hi_y, y_min, y_max)) continue;
-            const uint32_t bit = 1u << (k & 31u);
-            const uint32_t lane = k >> 5;
-            for (int oy = y_min; oy <= y_max; ++oy) {
-                const float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
-                const float dy_sq = __fmul_rn(dy, dy);
-                if (dy_sq > rec.radius_sq) continue;
-                uint32_t* row = bits + ((size_t)(oy - c.row_begin) * c.out_w) * lanes32 + lane;
-                for (int ox = x_min; ox <= x_max; ++ox) {
-                    const float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
-                    if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= rec.radius_sq) atomicOr(row + (size_t)ox * lanes32, bit);
+    const IDX xstep = (IDX)lanes32, ystep = (IDX)c.out_w * (IDX)lanes32;
+    for (uint32_t k0 = 0; k0 < c.n; k0 += FG_GW_OFF_CHUNK) {
+        const uint32_t kn = min((uint32_t)FG_GW_OFF_CHUNK, c.n - k0);
+        if (k0) __syncthreads();
+        for (uint32_t t = threadIdx.x; t < kn; t += 256) s_off[t] = __ldg(offsets + k0 + t);
+        __syncthreads();
+        // mask word of sample k0 in the row-band's first pixel; k0 is a multiple of 32
+        uint32_t* const bits0 = bits + (IDX)(k0 >> 5) - (IDX)c.row_begin * ystep;
+        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
+            const float4 rv = __ldg((const float4*)(grains + g));
+            const float cxz = rv.x, cyz = rv.y, R = rv.z, R2 = rv.w;
+            if (!(R > 0.0f)) continue;
+#pragma unroll 4
+            for (uint32_t k = 0; k < kn; ++k) {
+                const float2 o = s_off[k];
+                const float tx = __fadd_rn(cxz, o.x), ty = __fadd_rn(cyz, o.y);
+                int x_min, x_max, y_min, y_max;
+                gw_bounds_clip(tx, R, 0, last_x, x_min, x_max);
+                gw_bounds_clip(ty, R, lo_y, hi_y, y_min, y_max);
+                if (x_min > x_max || y_min > y_max) continue;
+                const uint32_t bit = 1u << (k & 31u);
+                uint32_t* p00 = bits0 + ((IDX)y_min * ystep + ((IDX)x_min * xstep + (IDX)(k >> 5)));
+                if (x_max - x_min <= 1 && y_max - y_min <= 1) {
+                    const float fx = __fadd_rn((float)x_min, 0.5f), fy = __fadd_rn((float)y_min, 0.5f);
+                    // (x_min + 1) + 0.5 == (x_min + 0.5) + 1 exactly: |x_min| < 2^22 here (clipped to the image)
+                    const float dx0 = __fsub_rn(fx, tx), dx1 = __fsub_rn(__fadd_rn((float)(x_min + 1), 0.5f), tx);
+                    const float dy0 = __fsub_rn(fy, ty), dy1 = __fsub_rn(__fadd_rn((float)(y_min + 1), 0.5f), ty);
+                    const float sx0 = __fmul_rn(dx0, dx0), sx1 = __fmul_rn(dx1, dx1);
+                    const float sy0 = __fmul_rn(dy0, dy0), sy1 = __fmul_rn(dy1, dy1);
+                    const bool x1 = x_max > x_min, y1 = y_max > y_min;
+                    if (__fadd_rn(sx0, sy0) <= R2) atomicOr(p00, bit);
+                    if (x1 && __fadd_rn(sx1, sy0) <= R2) atomicOr(p00 + xstep, bit);
+                    if (y1 && __fadd_rn(sx0, sy1) <= R2) atomicOr(p00 + ystep, bit);
+                    if (x1 && y1 && __fadd_rn(sx1, sy1) <= R2) atomicOr(p00 + ystep + xstep, bit);
+                    continue;
+                }
+                for (int oy = y_min; oy <= y_max; ++oy, p00 += ystep) {
+                    const float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
+                    const float dy_sq = __fmul_rn(dy, dy);
+                    if (dy_sq > R2) continue;
+                    uint32_t* p = p00;
+                    for (int ox = x_min; ox <= x_max; ++ox, p += xstep) {
+                        const float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
+                        if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= R2) atomicOr(p, bit);
+                    }
                 }
             }
         }

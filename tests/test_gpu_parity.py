@@ -401,3 +401,23 @@ def test_full_size_config3_grainwise_crop_consistency(ctx):
     for a, b in ((0, 300), (300, 301), (301, 1024)):
         ctx.render_grainwise(fg_params_from(p, d, rows=(a, b)), lam, off, out=banded)
     assert np.array_equal(banded, got)
+
+
+def test_multi_gpu_bands_into_peer_image_equal_single_gpu_render():
+    """N > 1 (needs >= 2 GPUs, skipped otherwise): every rank renders its row band straight into GPU 0's
+    peer-mapped image over NVLink (film_grain_b200/dist.py PeerImage) and, separately, through the NCCL
+    gather; both assembled images must be bitwise identical to the single-GPU render
+    (tools/p2p_check.py under torchrun, pixel-wise zoom 1 / zoom 2.5 and grain-wise)."""
+    import os
+    import subprocess
+    import sys
+
+    import film_grain_b200 as fg
+    if fg.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "p2p_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout and r.stdout.count("bitwise equal") >= 6, r.stdout
