@@ -203,75 +203,99 @@ __global__ void __launch_bounds__(256) k_gw_fill(const float* __restrict__ lambd
     }
 }
 
-// bounds() of src/grainwise.rs:126-142 without branches: [ceil((c-r)-0.5), floor((c+r)-0.5)] clipped to
-// [lo_lim, hi_lim]; the range is empty iff lo > hi afterwards (covers "max < min", "min > last" and
-// "max < 0": clipping one end only never turns an empty or outside range into a non-empty one).
-__device__ __forceinline__ void gw_bounds_clip(float center, float radius, int lo_lim, int hi_lim, int& lo, int& hi) {
-    lo = max(__float2int_ru(__fsub_rn(__fsub_rn(center, radius), 0.5f)), lo_lim);
-    hi = min(__float2int_rd(__fsub_rn(__fadd_rn(center, radius), 0.5f)), hi_lim);
-}
+// packed f32x2 arithmetic (one FADD2 / FMUL2 per pair; round-to-nearest per element, i.e. exactly the
+// two scalar operations of the reference)
+struct f32x2 { uint64_t v; };
+__device__ __forceinline__ f32x2 f2_make(float x, float y) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void f2_split(f32x2 a, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a.v)); }
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 
-// One thread per grain, looping over the N sample offsets (warp-uniform loads of offsets[k]):
-// rasterise the zoomed disk at centre+offset[k] and OR bit k into the per-pixel coverage mask
-// (src/grainwise.rs:66-101).  Lanes of a warp hold consecutive grains of the same input pixels, so
-// their atomics land on neighbouring mask words.  Boxes of at most 2 x 2 pixels (every disk of
-// diameter <= 1 output pixel, i.e. r * zoom <= 0.5) take a straight-line path: four predicated
-// tests and reductions, no loops and no divergent branches; larger boxes take the general loops.
-// The reference's per-row reject `dy_sq > radius_sq` is implied by the pixel test (dx*dx >= 0 and
-// round-to-nearest addition is monotone), so the straight-line path omits it.
-// IDX = uint32_t when the mask has fewer than 2^31 words, else size_t.
-#define FG_GW_OFF_CHUNK 2048 // sample offsets staged in shared memory per pass (16 KB)
+// One thread per grain, looping over the N sample offsets: rasterise the zoomed disk at
+// centre + offset[k] and OR bit k into the per-pixel coverage mask (src/grainwise.rs:66-101).
+//   * bounds() (src/grainwise.rs:126-142) without branches: [ceil((c-r)-0.5), floor((c+r)-0.5)] clipped
+//     to the image / row band by max/min; the range is empty iff lo > hi afterwards (clipping one end
+//     only never turns an empty or outside range into a non-empty one), x and y packed as f32x2;
+//   * a box of ONE pixel (every disk of diameter <= 1 output pixel, r * zoom <= 0.5, away from the exact
+//     half-pixel case) is one test and one reduction; boxes up to 2 x 2 are four predicated tests;
+//     larger boxes take the reference's loops.  The reference's per-row reject `dy_sq > radius_sq` is
+//     implied by the pixel test (dx*dx >= 0, round-to-nearest addition is monotone), so the
+//     straight-line paths omit it;
+//   * the offsets of the pass sit in shared memory and the next one is fetched while the current one is
+//     processed; the sample loop runs word by word of the mask (32 samples share a word index).
+// Lanes of a warp hold consecutive grains of the same input pixels, so their reductions land on
+// neighbouring mask words.  IDX = uint32_t when the whole image's mask has fewer than 2^32 words.
+#define FG_GW_OFF_CHUNK 2048 // sample offsets staged in shared memory per pass (16 KB), a multiple of 32
 template <typename IDX>
 __global__ void __launch_bounds__(256) k_gw_splat(const GrainRec* __restrict__ grains, const uint64_t* __restrict__ n_grains_ptr,
                                                    const float2* __restrict__ offsets, uint32_t* __restrict__ bits,
                                                    uint32_t lanes32, RenderConsts c) {
-    __shared__ float2 s_off[FG_GW_OFF_CHUNK];
+    __shared__ float2 s_off[FG_GW_OFF_CHUNK + 1];
     const uint64_t total = *n_grains_ptr;
     const int last_x = c.out_w - 1, lo_y = c.row_begin, hi_y = c.row_end - 1;
     const IDX xstep = (IDX)lanes32, ystep = (IDX)c.out_w * (IDX)lanes32;
+    const f32x2 half2 = f2_make(0.5f, 0.5f), one2 = f2_make(1.0f, 1.0f);
     for (uint32_t k0 = 0; k0 < c.n; k0 += FG_GW_OFF_CHUNK) {
         const uint32_t kn = min((uint32_t)FG_GW_OFF_CHUNK, c.n - k0);
         if (k0) __syncthreads();
-        for (uint32_t t = threadIdx.x; t < kn; t += 256) s_off[t] = __ldg(offsets + k0 + t);
+        for (uint32_t t = threadIdx.x; t <= kn; t += 256) s_off[t] = t < kn ? __ldg(offsets + k0 + t) : make_float2(0.0f, 0.0f);
         __syncthreads();
-        // mask word of sample k0 in the row-band's first pixel; k0 is a multiple of 32
+        // mask word of sample k0 in row 0 of the image (the band's mask starts at row_begin)
         uint32_t* const bits0 = bits + (IDX)(k0 >> 5) - (IDX)c.row_begin * ystep;
         for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (uint64_t)gridDim.x * blockDim.x) {
             const float4 rv = __ldg((const float4*)(grains + g));
-            const float cxz = rv.x, cyz = rv.y, R = rv.z, R2 = rv.w;
+            const float R = rv.z, R2 = rv.w;
             if (!(R > 0.0f)) continue;
+            const f32x2 ctr = f2_make(rv.x, rv.y), rr = f2_make(R, R);
+            float2 o = s_off[0];
+            for (uint32_t kw = 0; kw < kn; kw += 32) {
+                uint32_t* const bw = bits0 + (IDX)(kw >> 5);
+                const uint32_t ke = min(32u, kn - kw);
 #pragma unroll 4
-            for (uint32_t k = 0; k < kn; ++k) {
-                const float2 o = s_off[k];
-                const float tx = __fadd_rn(cxz, o.x), ty = __fadd_rn(cyz, o.y);
-                int x_min, x_max, y_min, y_max;
-                gw_bounds_clip(tx, R, 0, last_x, x_min, x_max);
-                gw_bounds_clip(ty, R, lo_y, hi_y, y_min, y_max);
-                if (x_min > x_max || y_min > y_max) continue;
-                const uint32_t bit = 1u << (k & 31u);
-                uint32_t* p00 = bits0 + ((IDX)y_min * ystep + ((IDX)x_min * xstep + (IDX)(k >> 5)));
-                if (x_max - x_min <= 1 && y_max - y_min <= 1) {
-                    const float fx = __fadd_rn((float)x_min, 0.5f), fy = __fadd_rn((float)y_min, 0.5f);
-                    // (x_min + 1) + 0.5 == (x_min + 0.5) + 1 exactly: |x_min| < 2^22 here (clipped to the image)
-                    const float dx0 = __fsub_rn(fx, tx), dx1 = __fsub_rn(__fadd_rn((float)(x_min + 1), 0.5f), tx);
-                    const float dy0 = __fsub_rn(fy, ty), dy1 = __fsub_rn(__fadd_rn((float)(y_min + 1), 0.5f), ty);
-                    const float sx0 = __fmul_rn(dx0, dx0), sx1 = __fmul_rn(dx1, dx1);
-                    const float sy0 = __fmul_rn(dy0, dy0), sy1 = __fmul_rn(dy1, dy1);
-                    const bool x1 = x_max > x_min, y1 = y_max > y_min;
-                    if (__fadd_rn(sx0, sy0) <= R2) atomicOr(p00, bit);
-                    if (x1 && __fadd_rn(sx1, sy0) <= R2) atomicOr(p00 + xstep, bit);
-                    if (y1 && __fadd_rn(sx0, sy1) <= R2) atomicOr(p00 + ystep, bit);
-                    if (x1 && y1 && __fadd_rn(sx1, sy1) <= R2) atomicOr(p00 + ystep + xstep, bit);
-                    continue;
-                }
-                for (int oy = y_min; oy <= y_max; ++oy, p00 += ystep) {
-                    const float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
-                    const float dy_sq = __fmul_rn(dy, dy);
-                    if (dy_sq > R2) continue;
-                    uint32_t* p = p00;
-                    for (int ox = x_min; ox <= x_max; ++ox, p += xstep) {
-                        const float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
-                        if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= R2) atomicOr(p, bit);
+                for (uint32_t kb = 0; kb < ke; ++kb) {
+                    const f32x2 t = f2_add(ctr, f2_make(o.x, o.y)); // (tx, ty) = (cx*zoom + ox, cy*zoom + oy)
+                    o = s_off[kw + kb + 1];                         // next sample's offset (entry kn is padding)
+                    float lx, ly, hx, hy;
+                    f2_split(f2_sub(f2_sub(t, rr), half2), lx, ly);
+                    f2_split(f2_sub(f2_add(t, rr), half2), hx, hy);
+                    const int x_min = max(__float2int_ru(lx), 0), x_max = min(__float2int_rd(hx), last_x);
+                    const int y_min = max(__float2int_ru(ly), lo_y), y_max = min(__float2int_rd(hy), hi_y);
+                    const int wx = x_max - x_min, wy = y_max - y_min;
+                    if ((wx | wy) < 0) continue; // empty in x or y
+                    const uint32_t bit = 1u << kb;
+                    const IDX i00 = (IDX)y_min * ystep + (IDX)x_min * xstep;
+                    const f32x2 f0 = f2_add(f2_make((float)x_min, (float)y_min), half2); // pixel centre (ox + 0.5, oy + 0.5)
+                    float sx0, sy0;
+                    f2_split(f2_mul(f2_sub(f0, t), f2_sub(f0, t)), sx0, sy0);
+                    if ((wx | wy) == 0) { // one pixel
+                        if (__fadd_rn(sx0, sy0) <= R2) atomicOr(bw + i00, bit);
+                        continue;
+                    }
+                    if (wx <= 1 && wy <= 1) {
+                        // (ox + 1) + 0.5 == (ox + 0.5) + 1 exactly: |ox| < 2^22 after clipping to the image
+                        const f32x2 f1 = f2_add(f0, one2);
+                        float sx1, sy1;
+                        f2_split(f2_mul(f2_sub(f1, t), f2_sub(f1, t)), sx1, sy1);
+                        const bool x1 = wx > 0, y1 = wy > 0;
+                        if (__fadd_rn(sx0, sy0) <= R2) atomicOr(bw + i00, bit);
+                        if (x1 && __fadd_rn(sx1, sy0) <= R2) atomicOr(bw + (i00 + xstep), bit);
+                        if (y1 && __fadd_rn(sx0, sy1) <= R2) atomicOr(bw + (i00 + ystep), bit);
+                        if (x1 && y1 && __fadd_rn(sx1, sy1) <= R2) atomicOr(bw + (i00 + ystep + xstep), bit);
+                        continue;
+                    }
+                    float tx, ty;
+                    f2_split(t, tx, ty);
+                    uint32_t* p00 = bw + i00;
+                    for (int oy = y_min; oy <= y_max; ++oy, p00 += ystep) {
+                        const float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
+                        const float dy_sq = __fmul_rn(dy, dy);
+                        if (dy_sq > R2) continue;
+                        uint32_t* p = p00;
+                        for (int ox = x_min; ox <= x_max; ++ox, p += xstep) {
+                            const float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
+                            if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= R2) atomicOr(p, bit);
+                        }
                     }
                 }
             }

@@ -207,6 +207,9 @@ GRAIN_CASES = [
     ("r0.1_bigq", 16, 16, dict(radius=0.1, n_samples=8)),
     ("lognorm", 32, 32, dict(radius=0.4, radius_dist=O.DIST_LOGNORM, radius_stddev=0.3, n_samples=8)),
     ("zoom0.6_size", 40, 30, dict(radius=0.8, n_samples=8, zoom=0.6, size=(31, None))),
+    ("r0.4_zoom1.5_box2x2", 48, 40, dict(radius=0.4, n_samples=40, zoom=1.5)),  # R = 0.6: boxes of 1-2 pixels per axis
+    ("r0.7_box2x2", 40, 36, dict(radius=0.7, n_samples=33)),
+    ("r0.5_N2100_two_offset_passes", 20, 16, dict(radius=0.5, n_samples=2100)),  # > 2048 offsets: second shared-memory pass
 ]
 
 
