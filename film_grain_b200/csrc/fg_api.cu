@@ -12,6 +12,7 @@
 #include "fg_ctx.cuh"
 #include "fg_kernels.cuh"
 #include "fg_tile.cuh"
+#include "fg_gw_tile.cuh"
 #include "fg_color.cuh"
 #include "fg_zig_tables.h"
 #include <algorithm>
@@ -148,10 +149,17 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     const size_t npix_in = (size_t)(iy1 - iy0) * p->in_w;
     const uint32_t lanes32 = (p->n_samples + 31) / 32;
     const size_t band_pix = (size_t)(c.row_end - c.row_begin) * p->out_w;
+    // Tiled rasteriser (coverage masks in shared memory, fg_gw_tile.cuh) whenever a tile's input footprint is
+    // bounded; fg_params.path == FG_PATH_DIRECT (tests) or an extreme zoom-out / radius selects the global-mask kernels.
+    const double rmax = (double)p->rm * p->zoom;
+    const double foot_rows = ((double)FG_GT_H + 2.0 + ((double)c.off_max_y - (double)c.off_min_y) + 2.0 * rmax) / p->zoom + 8.0;
+    const bool tiled = p->path != FG_PATH_DIRECT && foot_rows <= (double)FG_GT_MAXROWS && rmax < 4096.0;
     int rc;
-    if ((rc = ensure(ctx, ctx->bits, band_pix * lanes32 * sizeof(uint32_t)))) return rc;
     if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
-    FG_CUDA(ctx, cudaMemsetAsync(ctx->bits.p, 0, band_pix * lanes32 * sizeof(uint32_t), ctx->stream));
+    if (!tiled) {
+        if ((rc = ensure(ctx, ctx->bits, band_pix * lanes32 * sizeof(uint32_t)))) return rc;
+        FG_CUDA(ctx, cudaMemsetAsync(ctx->bits.p, 0, band_pix * lanes32 * sizeof(uint32_t), ctx->stream));
+    }
     uint64_t* d_total = (uint64_t*)ctx->misc.p;
     uint64_t total = 0;
     if (npix_in > 0) {
@@ -174,18 +182,34 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
             if ((rc = ensure(ctx, ctx->grains, total * sizeof(GrainRec)))) return rc;
             k_gw_fill<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (const uint64_t*)ctx->scan_out.p, (GrainRec*)ctx->grains.p, c);
             FG_CUDA(ctx, cudaGetLastError());
-            uint64_t want_blocks = (total + 255) / 256;
-            const uint64_t max_blocks = (uint64_t)ctx->sm_count * 64;
-            unsigned sblocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-            if ((size_t)p->out_w * p->out_h * lanes32 < ((size_t)1 << 32)) // word indices relative to row 0 fit 32 bits
-                k_gw_splat<uint32_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
-                                                                       (uint32_t*)ctx->bits.p, lanes32, c);
-            else
-                k_gw_splat<size_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
-                                                                     (uint32_t*)ctx->bits.p, lanes32, c);
-            FG_CUDA(ctx, cudaGetLastError());
-            ctx->stats.launches += 2;
+            ctx->stats.launches += 1;
+            if (!tiled) {
+                uint64_t want_blocks = (total + 255) / 256;
+                const uint64_t max_blocks = (uint64_t)ctx->sm_count * 64;
+                unsigned sblocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
+                if ((size_t)p->out_w * p->out_h * lanes32 < ((size_t)1 << 32)) // word indices relative to row 0 fit 32 bits
+                    k_gw_splat<uint32_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
+                                                                           (uint32_t*)ctx->bits.p, lanes32, c);
+                else
+                    k_gw_splat<size_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
+                                                                         (uint32_t*)ctx->bits.p, lanes32, c);
+                FG_CUDA(ctx, cudaGetLastError());
+                ctx->stats.launches += 1;
+            }
         }
+    } else {
+        FG_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint64_t), ctx->stream));
+    }
+    if (tiled) {
+        const int tiles_x = (int)((p->out_w + FG_GT_W - 1) / FG_GT_W), tiles_y = (c.row_end - c.row_begin + FG_GT_H - 1) / FG_GT_H;
+        if (tiles_x > 0 && tiles_y > 0) {
+            k_gw_tile<<<(unsigned)tiles_x * (unsigned)tiles_y, FG_GT_THREADS, sizeof(GwTileSmem), ctx->stream>>>(
+                (const GrainRec*)ctx->grains.p, (const uint64_t*)ctx->scan_out.p, npix_in, d_total, iy0, iy1, (const float2*)d_offsets,
+                d_out, tiles_x, c);
+            FG_CUDA(ctx, cudaGetLastError());
+            ctx->stats.launches += 1;
+        }
+        return FG_OK;
     }
     k_gw_reduce<<<(unsigned)((band_pix + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->bits.p, lanes32, d_out, c);
     FG_CUDA(ctx, cudaGetLastError());
@@ -311,6 +335,10 @@ int fg_context_create(fg_ctx** out, int device) {
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     int rc = tile_setup(ctx);
+    if (!rc && cudaFuncSetAttribute(k_gw_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GwTileSmem)) != cudaSuccess) {
+        cudaGetLastError();
+        rc = FG_ERR_CUDA_STICKY;
+    }
     if (rc) { fg_context_destroy(ctx); return rc; }
     *out = ctx;
     return FG_OK;

@@ -210,16 +210,21 @@ GRAIN_CASES = [
     ("r0.4_zoom1.5_box2x2", 48, 40, dict(radius=0.4, n_samples=40, zoom=1.5)),  # R = 0.6: boxes of 1-2 pixels per axis
     ("r0.7_box2x2", 40, 36, dict(radius=0.7, n_samples=33)),
     ("r0.5_N2100_two_offset_passes", 20, 16, dict(radius=0.5, n_samples=2100)),  # > 2048 offsets: second shared-memory pass
+    ("r0.5_multi_tile", 300, 150, dict(radius=0.5, n_samples=8)),                 # 3 x 3 output tiles of 128 x 64
+    ("r0.3_zoom2_multi_tile", 100, 70, dict(radius=0.3, n_samples=36, zoom=2.0)),
 ]
 
 
+@pytest.mark.parametrize("path", [0, 1], ids=["tiled", "global_mask"])
 @pytest.mark.parametrize("name,w,h,kw", GRAIN_CASES, ids=[c[0] for c in GRAIN_CASES])
-def test_grainwise_matches_oracle(ctx, name, w, h, kw):
+def test_grainwise_matches_oracle(ctx, name, w, h, kw, path):
+    """path 0: one CTA per output tile, coverage masks in shared memory (k_gw_tile); path 1
+    (FG_PATH_DIRECT): the global-mask kernels (k_gw_splat + k_gw_reduce)."""
     p = O.make_params(algo=O.ALGO_GRAIN, **kw)
     d, off, off_in = O.derive_common(p, w, h)
     lam = lambda_from_u8(noise_u8(w, h, seed=5)[:, :, 1], d.inv_e_pi_r2)
     ref = O.render_grainwise(lam, p, d, off)
-    got = ctx.render_grainwise(fg_params_from(p, d), lam, off)
+    got = ctx.render_grainwise(fg_params_from(p, d, path=path), lam, off)
     assert np.array_equal(ref, got), f"{np.count_nonzero(ref != got)} px differ, max {np.abs(ref - got).max()}"
     assert 0.0 < ref.mean() < 1.0
 
