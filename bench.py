@@ -439,6 +439,30 @@ def main():
                     "hbm": {"achieved_gbs": io_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                             "frac": io_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if os.path.exists(peaks_file) else "fallback"}}
+        if wl["algo"] == "grain":
+            # unit = one (grain, sample) disk rasterisation, 14 lane-ops of set-up + 5 per box pixel
+            # (a box holds (2R)^2 pixel centres on average), plus A_gen = 200 per input pixel for the generation.
+            # Grain count = the Poisson means' sum (the realised count differs by < 1e-3 relative).
+            grains = float(sum(float(np.asarray(l, np.float64).sum()) for l in lam_host))
+            r_out = float(min(wl["radius"], float(d.rm))) * wl["zoom"]
+            pairs = grains * wl["n"]
+            ops_r = pairs * (14.0 + 5.0 * (2.0 * r_out) ** 2)
+            ops_g = 200.0 * planes * wl["w"] * wl["h"]
+            kernel_ms = (strip_total_ms / args.steps) if strip_total_ms > 0 else ms_per_step
+            tab_ms = table_total_ms / args.steps
+            peak = issue["ffma"] / 1e3 * world
+            achieved = ops_r / (kernel_ms * 1e-3) / 1e12
+            roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "k_gw_tile (last plane)", "kernel_ms": kernel_ms, "share_of_step": kernel_ms * planes / ms_per_step,
+                    "launches_per_step": planes,
+                    "generation": {"kernels": "k_gw_count + scan + k_gw_fill", "ms": tab_ms,
+                                   "achieved": (ops_g / planes / (tab_ms * 1e-3) / 1e12) if tab_ms > 0 else None},
+                    "pipeline": {"achieved": (ops_r + ops_g) / (ms_per_step * 1e-3) / 1e12,
+                                 "frac": (ops_r + ops_g) / (ms_per_step * 1e-3) / 1e12 / peak},
+                    "ops_model": {"A_setup": 14, "A_pixel": 5, "A_gen": 200, "grains": grains, "pairs": pairs,
+                                  "box_pixels": (2.0 * r_out) ** 2, "ops_raster": ops_r, "ops_gen": ops_g},
+                    "peak_source": "FFMA issue rate measured in this run (fg_measure_issue_peak)",
+                    "issue_peaks_glaneops": issue}
         line = {
             "metric": "Mpixel*samples/s", "value": value, "unit": "Mpixel*samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -162,6 +162,8 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     }
     uint64_t* d_total = (uint64_t*)ctx->misc.p;
     uint64_t total = 0;
+    bool ev4 = false;
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream)); // ev[6]..ev[4]: grain generation, ev[4]..ev[5]: rasterisation
     if (npix_in > 0) {
         if ((rc = ensure(ctx, ctx->counts, npix_in * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->scan_out, npix_in * sizeof(uint64_t)))) return rc;
@@ -183,6 +185,8 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
             k_gw_fill<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (const uint64_t*)ctx->scan_out.p, (GrainRec*)ctx->grains.p, c);
             FG_CUDA(ctx, cudaGetLastError());
             ctx->stats.launches += 1;
+            FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+            ev4 = true;
             if (!tiled) {
                 uint64_t want_blocks = (total + 255) / 256;
                 const uint64_t max_blocks = (uint64_t)ctx->sm_count * 64;
@@ -200,6 +204,10 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     } else {
         FG_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint64_t), ctx->stream));
     }
+    if (!ev4) FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    ctx->fb_count_host = 0; // fg_get_stats: strip_ms = rasterisation, table_ms = grain generation of the last plane
+    ctx->strip_launches = 1;
+    ctx->fb_pending = true;
     if (tiled) {
         const int tiles_x = (int)((p->out_w + FG_GT_W - 1) / FG_GT_W), tiles_y = (c.row_end - c.row_begin + FG_GT_H - 1) / FG_GT_H;
         if (tiles_x > 0 && tiles_y > 0) {
@@ -209,10 +217,12 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
             FG_CUDA(ctx, cudaGetLastError());
             ctx->stats.launches += 1;
         }
+        FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
         return FG_OK;
     }
     k_gw_reduce<<<(unsigned)((band_pix + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->bits.p, lanes32, d_out, c);
     FG_CUDA(ctx, cudaGetLastError());
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->stats.launches += 1;
     return FG_OK;
 }

@@ -97,9 +97,9 @@ typedef struct fg_stats {
     uint32_t tiles_total;     /* pixel-wise tiled path: tiles rendered */
     uint32_t tiles_fallback;  /*   of which re-rendered by the direct kernel (capacity / lambda>=12) */
     uint64_t h2d_bytes, d2h_bytes;
-    float strip_ms;           /* pixel-wise tiled path: device time of the (last) strip-kernel launch */
+    float strip_ms;           /* pixel-wise tiled path: device time of the (last) strip-kernel launch; grain-wise: of the rasterisation (last plane) */
     uint32_t strip_launches;  /*   strip-kernel launches of the call (row sub-bands; normally 1) */
-    float table_ms;           /*   device time of the (last) band's thresholds + bitmap + cell-table kernels */
+    float table_ms;           /*   device time of the (last) band's thresholds + bitmap + cell-table kernels; grain-wise: grain generation */
     uint32_t reserved;
 } fg_stats;
 
