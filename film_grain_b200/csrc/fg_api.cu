@@ -242,6 +242,26 @@ int render_planes_device_locked(fg_ctx* ctx, const fg_params* p, const RenderCon
     return FG_OK;
 }
 
+// Output planes that form ONE contiguous block of page-locked host memory mapped into the device's address
+// space (cudaHostAlloc / cudaHostRegister; unified addressing): the kernels can store their results
+// straight into it, so the device->host transfer of the image happens during the render instead of after
+// it.  Returns the device-side pointer of the block, or nullptr (pageable or scattered planes: staged copy).
+float* mapped_host_planes(float* const* out, int n_planes, size_t out_elems) {
+    static const bool enabled = !(std::getenv("FG_B200_ZEROCOPY") && std::atoi(std::getenv("FG_B200_ZEROCOPY")) == 0);
+    if (!enabled) return nullptr;
+    for (int pl = 1; pl < n_planes; ++pl)
+        if (out[pl] != out[0] + out_elems * pl) return nullptr;
+    cudaPointerAttributes first{}, last{};
+    if (cudaPointerGetAttributes(&first, out[0]) != cudaSuccess ||
+        cudaPointerGetAttributes(&last, (const char*)out[0] + out_elems * n_planes * sizeof(float) - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (first.type != cudaMemoryTypeHost || last.type != cudaMemoryTypeHost || !first.devicePointer || !last.devicePointer) return nullptr;
+    if ((const char*)last.devicePointer - (const char*)first.devicePointer != (ptrdiff_t)(out_elems * n_planes * sizeof(float) - 1)) return nullptr;
+    return (float*)first.devicePointer;
+}
+
 int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
                        const float* offsets, float* const* out) {
     if (!ctx) return FG_ERR_INVALID;
@@ -261,7 +281,9 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
     RenderConsts c = make_consts(p, offsets);
     const size_t in_elems = (size_t)p->in_w * p->in_h, out_elems = (size_t)p->out_w * p->out_h;
     if ((rc = ensure(ctx, ctx->lambda, in_elems * n_planes * sizeof(float)))) return rc;
-    if ((rc = ensure(ctx, ctx->out, out_elems * n_planes * sizeof(float)))) return rc;
+    float* const mapped = mapped_host_planes(out, n_planes, out_elems);
+    if (!mapped && (rc = ensure(ctx, ctx->out, out_elems * n_planes * sizeof(float)))) return rc;
+    float* const d_dst = mapped ? mapped : (float*)ctx->out.p;
     if ((rc = ensure(ctx, ctx->offsets, (size_t)p->n_samples * 2 * sizeof(float)))) return rc;
     cudaStream_t s = ctx->stream;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
@@ -269,11 +291,11 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
         FG_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lambda.p + in_elems * pl, lambda[pl], in_elems * sizeof(float), cudaMemcpyHostToDevice, s));
     FG_CUDA(ctx, cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)p->n_samples * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
-    rc = render_planes_device_locked(ctx, p, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, (float*)ctx->out.p);
+    rc = render_planes_device_locked(ctx, p, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, d_dst);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
     const size_t band_off = (size_t)c.row_begin * p->out_w, band_elems = (size_t)(c.row_end - c.row_begin) * p->out_w;
-    for (int pl = 0; pl < n_planes; ++pl)
+    for (int pl = 0; pl < n_planes && !mapped; ++pl) // mapped: the kernels' own stores were the transfer
         FG_CUDA(ctx, cudaMemcpyAsync(out[pl] + band_off, (float*)ctx->out.p + out_elems * pl + band_off, band_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
     FG_CUDA(ctx, cudaStreamSynchronize(s));

@@ -429,3 +429,37 @@ def test_multi_gpu_bands_into_peer_image_equal_single_gpu_render():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout and r.stdout.count("bitwise equal") >= 6, r.stdout
+
+
+@pytest.mark.parametrize("algo", ["pixel", "grain"])
+def test_pinned_contiguous_output_planes_are_written_in_place(ctx, algo):
+    """fg_render_planes with output planes that are one block of page-locked host memory: the kernels store
+    straight into the mapped block (no staged device->host copy); the result equals the pageable-buffer call
+    and the oracle, for a full render and for a row band (rows outside the band stay untouched)."""
+    import torch
+    w, h = 200, 120
+    if algo == "pixel":
+        p = O.make_params(radius=0.1, n_samples=24, algo=O.ALGO_PIXEL)
+    else:
+        p = O.make_params(radius=0.5, n_samples=40, algo=O.ALGO_GRAIN)
+    d, off, off_in = O.derive_common(p, w, h)
+    offs = off_in if algo == "pixel" else off
+    a = O.ALGO_PIXEL if algo == "pixel" else O.ALGO_GRAIN
+    img = noise_u8(w, h, seed=11)
+    lams = [lambda_from_u8(img[:, :, c], d.inv_e_pi_r2) for c in range(3)]
+    ref = ctx.render_planes(fg_params_from(p, d), a, lams, offs)
+    oracle0 = O.render_pixelwise(lams[0], p, d, off_in) if algo == "pixel" else O.render_grainwise(lams[0], p, d, off)
+    assert np.array_equal(ref[0], oracle0)
+    pin = torch.full((3, d.output_height, d.output_width), -7.0, dtype=torch.float32).pin_memory()
+    outs = [pin[c].numpy() for c in range(3)]
+    ctx.render_planes(fg_params_from(p, d), a, lams, offs, outs)
+    st = ctx.stats()
+    for c in range(3):
+        assert np.array_equal(outs[c], ref[c])
+    assert st.d2h_bytes == 3 * d.output_height * d.output_width * 4
+    pin.fill_(-7.0)
+    rows = (37, 90)
+    ctx.render_planes(fg_params_from(p, d, rows=rows), a, lams, offs, outs)
+    for c in range(3):
+        assert np.array_equal(outs[c][rows[0]:rows[1]], ref[c][rows[0]:rows[1]])
+        assert np.all(outs[c][:rows[0]] == -7.0) and np.all(outs[c][rows[1]:] == -7.0)
