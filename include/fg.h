@@ -131,7 +131,11 @@ int fg_render_grainwise(fg_ctx* ctx, const fg_params* p, const float* lambda,
 
 /* n_planes planes in one call with shared parameters (RGB renders 3 planes with the same
  * seed and offsets, src/color.rs:56-60): one upload, one batched launch, one download.
- * algo = FG_ALGO_PIXEL (offsets = offsets_input) or FG_ALGO_GRAIN (offsets = offsets). */
+ * algo = FG_ALGO_PIXEL (offsets = offsets_input) or FG_ALGO_GRAIN (offsets = offsets).
+ * When the output planes are one contiguous block of page-locked host memory (cudaHostAlloc /
+ * cudaHostRegister; out[pl] == out[0] + pl*out_w*out_h) the kernels store their results straight
+ * into it over PCIe while they run, instead of a staged device->host copy afterwards; pageable or
+ * scattered planes take the staged copy.  Same results either way. */
 int fg_render_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes,
                      const float* const* lambda, const float* offsets, float* const* out);
 
