@@ -358,38 +358,70 @@ def main():
                                  "h2d_bytes_per_step": int(s8.h2d_bytes), "d2h_bytes_per_step": int(s8.d2h_bytes),
                                  "call": "fg_render_rgb8 (host u8 RGB in/out, colour fused on device)"}
     else:
-        # each rank uploads only the lambda rows its band can see: band / zoom +- (max |offset| + rm) plus slack
-        reach = float(np.abs(d.offsets_input[:, 1]).max()) + float(d.rm) + 2.0
-        in_r0 = max(0, int(np.floor(rb / wl["zoom"] - reach)))
-        in_r1 = min(wl["h"], int(np.ceil(re / wl["zoom"] + reach)) + 1)
-        pin_in = torch.from_numpy(np.stack(lam_host)[:, in_r0:in_r1, :].copy()).pin_memory()
-        pin_shape = (planes, out_h, out_w) if peer is not None else (out_h, planes, out_w)
-        pin_out = torch.empty(pin_shape, dtype=torch.float32).pin_memory() if rank == 0 else None
-        with torch.cuda.stream(stream):
+        from film_grain_b200.dist import SharedHostImage
+        shared = SharedHostImage.create((planes, out_h, out_w), rank, world, dev) if args.bands != "gather" else None
+        if shared is not None:
+            # The reference-facing host call on every rank: fg_render_planes with the rank's row band, pinned
+            # lambda planes in (the engine uploads only the input rows the band reads) and the planes of ONE
+            # page-locked host image shared by all ranks out (the kernels store the band rows straight into
+            # it, each GPU over its own PCIe link); a barrier ends the step with the whole image in host memory.
+            pin_lam = torch.from_numpy(np.stack(lam_host)).pin_memory()
+            lam_pinned = [pin_lam[c].numpy() for c in range(planes)]
+            host_outs = [shared.array[c] for c in range(planes)]
+
             def step_e2e():
-                if peer is not None:
-                    peer.finish()  # GPU 0 has read the previous image out before anyone overwrites it
-                d_lam[:, in_r0:in_r1, :].copy_(pin_in, non_blocking=True)
-                full = step_device()
-                if rank == 0:
-                    pin_out.copy_(full, non_blocking=True)
-            step_e2e()
-            stream.synchronize()
-            dist.barrier()
+                ctx.render_planes(blk, algo, lam_pinned, offsets, host_outs)
+                dist.barrier()
+            for _ in range(2):
+                step_e2e()
             t0 = time.perf_counter()
             for _ in range(args.steps):
                 step_e2e()
-                stream.synchronize()
-            dist.barrier()
             e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t2[0])
-        e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
-               "h2d_bytes_per_step": int(pin_in.numel() * 4), "d2h_bytes_per_step": int(planes * out_w * out_h * 4),
-               "ms_per_step": e2e_ms,
-               "call": "per rank: pinned H2D of the lambda rows its band sees + band render + "
-                       + ("peer stores into GPU 0's image + barrier" if peer is not None else "NCCL band gather") + "; rank 0: D2H of the image"}
+            s = ctx.stats()
+            tb = torch.tensor([e2e_ms, float(s.h2d_bytes), float(s.d2h_bytes)], dtype=torch.float64, device=dev)
+            tmax = tb.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+            e2e_ms = float(tmax[0])
+            e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
+                   "h2d_bytes_per_step": int(tb[1]), "d2h_bytes_per_step": int(tb[2]), "ms_per_step": e2e_ms,
+                   "call": "per rank: fg_render_planes on its row band (pinned host lambda in, band-restricted upload; output = one "
+                           "page-locked host image shared by all ranks, written in place by the kernels) + barrier; bytes summed over ranks"}
+            shared.close()
+        else:
+            # each rank uploads only the lambda rows its band can see: band / zoom +- (max |offset| + rm) plus slack
+            reach = float(np.abs(d.offsets_input[:, 1]).max()) + float(d.rm) + 2.0
+            in_r0 = max(0, int(np.floor(rb / wl["zoom"] - reach)))
+            in_r1 = min(wl["h"], int(np.ceil(re / wl["zoom"] + reach)) + 1)
+            pin_in = torch.from_numpy(np.stack(lam_host)[:, in_r0:in_r1, :].copy()).pin_memory()
+            pin_shape = (planes, out_h, out_w) if peer is not None else (out_h, planes, out_w)
+            pin_out = torch.empty(pin_shape, dtype=torch.float32).pin_memory() if rank == 0 else None
+            with torch.cuda.stream(stream):
+                def step_e2e():
+                    if peer is not None:
+                        peer.finish()  # GPU 0 has read the previous image out before anyone overwrites it
+                    d_lam[:, in_r0:in_r1, :].copy_(pin_in, non_blocking=True)
+                    full = step_device()
+                    if rank == 0:
+                        pin_out.copy_(full, non_blocking=True)
+                step_e2e()
+                stream.synchronize()
+                dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    step_e2e()
+                    stream.synchronize()
+                dist.barrier()
+                e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t2[0])
+            e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
+                   "h2d_bytes_per_step": int(pin_in.numel() * 4), "d2h_bytes_per_step": int(planes * out_w * out_h * 4),
+                   "ms_per_step": e2e_ms,
+                   "call": "per rank: pinned H2D of the lambda rows its band sees + band render + "
+                           + ("peer stores into GPU 0's image + barrier" if peer is not None else "NCCL band gather") + "; rank 0: D2H of the image"}
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")

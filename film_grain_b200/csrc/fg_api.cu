@@ -242,6 +242,28 @@ int render_planes_device_locked(fg_ctx* ctx, const fg_params* p, const RenderCon
     return FG_OK;
 }
 
+// Input rows [r0, r1) a render of the band [c.row_begin, c.row_end) can read (everything for a full render).
+// Pixel-wise: the cells within rm of the band's sample points map to input rows floor(j * delta), clamped
+// (src/pixelwise.rs:55-73); the cell table adds two cells and a row of slack on each side.  Grain-wise: the
+// rows whose grains can reach the band (the same expression as grainwise_device_plane).
+void input_rows_of_band(const fg_params* p, const RenderConsts& c, int algo, int& r0, int& r1) {
+    r0 = 0; r1 = (int)p->in_h;
+    if (c.row_begin <= 0 && c.row_end >= (int)p->out_h) return;
+    double lo, hi;
+    if (algo == FG_ALGO_PIXEL) {
+        const double slack = 2.0 * (double)p->delta + 4.0;
+        lo = ((double)c.row_begin + 0.5) / p->zoom - (double)c.off_max_y - (double)p->rm - slack;
+        hi = ((double)c.row_end - 0.5) / p->zoom - (double)c.off_min_y + (double)p->rm + slack + 1.0;
+    } else {
+        const double reach = (double)p->rm * p->zoom + 2.0;
+        lo = ((double)c.row_begin - reach - (double)c.off_max_y) / p->zoom - 3.0;
+        hi = ((double)c.row_end + reach - (double)c.off_min_y) / p->zoom + 3.0;
+    }
+    if (lo > 0.0) r0 = lo < (double)p->in_h ? (int)lo : (int)p->in_h - 1; // clamped lookups read the edge rows
+    if (hi < (double)p->in_h) r1 = hi > 1.0 ? (int)hi : 1;
+    if (r1 <= r0) { r0 = 0; r1 = (int)p->in_h; }
+}
+
 // Output planes that form ONE contiguous block of page-locked host memory mapped into the device's address
 // space (cudaHostAlloc / cudaHostRegister; unified addressing): the kernels can store their results
 // straight into it, so the device->host transfer of the image happens during the render instead of after
@@ -287,8 +309,14 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
     if ((rc = ensure(ctx, ctx->offsets, (size_t)p->n_samples * 2 * sizeof(float)))) return rc;
     cudaStream_t s = ctx->stream;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+    // a row band uploads only the input rows it can read
+    int in_r0, in_r1;
+    input_rows_of_band(p, c, algo, in_r0, in_r1);
+    static const bool poison = std::getenv("FG_B200_POISON") && std::atoi(std::getenv("FG_B200_POISON")) != 0; // tests: NaN outside the uploaded rows
+    if (poison) FG_CUDA(ctx, cudaMemsetAsync(ctx->lambda.p, 0xFF, in_elems * n_planes * sizeof(float), s));
+    const size_t up_off = (size_t)in_r0 * p->in_w, up_elems = (size_t)(in_r1 - in_r0) * p->in_w;
     for (int pl = 0; pl < n_planes; ++pl)
-        FG_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lambda.p + in_elems * pl, lambda[pl], in_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+        FG_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lambda.p + in_elems * pl + up_off, lambda[pl] + up_off, up_elems * sizeof(float), cudaMemcpyHostToDevice, s));
     FG_CUDA(ctx, cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)p->n_samples * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
     rc = render_planes_device_locked(ctx, p, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, d_dst);
@@ -302,7 +330,7 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
     cudaEventElapsedTime(&ctx->stats.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->stats.d2h_ms, ctx->ev[2], ctx->ev[3]);
-    ctx->stats.h2d_bytes = (in_elems * n_planes + (size_t)p->n_samples * 2) * sizeof(float);
+    ctx->stats.h2d_bytes = (up_elems * n_planes + (size_t)p->n_samples * 2) * sizeof(float);
     ctx->stats.d2h_bytes = band_elems * n_planes * sizeof(float);
     if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
     return FG_OK;

@@ -121,3 +121,69 @@ class PeerImage:
                 import sys
                 print(f"[film_grain_b200.dist] peer image mode {mode!r} unavailable: {err!r}", file=sys.stderr)
         return None
+
+
+class SharedHostImage:
+    """The finished image in page-locked HOST memory shared by every rank of the box.
+
+    One /dev/shm mapping, registered with cudaHostRegister (portable, mapped) in every process.  Each rank
+    passes the planes of this block as the `out` buffers of the host-pointer C-ABI call
+    (`fg_render_planes` with its row band): the engine recognises page-locked output and lets the kernels
+    store the band rows straight into it, so every GPU delivers its band over its own PCIe link while it
+    renders and nothing funnels through GPU 0.  After a barrier the whole image is in host memory.
+    `create` returns None when the mapping cannot be set up on every rank.
+    """
+
+    def __init__(self, array, path, owner):
+        self.array, self._path, self._owner = array, path, owner
+
+    @classmethod
+    def create(cls, shape, rank: int, world: int, device, group=None):
+        import os
+        import uuid
+
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        tag = [uuid.uuid4().hex if rank == 0 else None]
+        if world > 1:
+            dist.broadcast_object_list(tag, src=0, group=group)
+        path = f"/dev/shm/fg_b200_{tag[0]}"
+        made, err = None, None
+        try:
+            if rank == 0:
+                arr = np.lib.format.open_memmap(path, mode="w+", dtype=np.float32, shape=tuple(shape))
+                arr[...] = 0.0
+            if world > 1:
+                dist.barrier(group=group)
+            if rank != 0:
+                arr = np.load(path, mmap_mode="r+")
+            rc = torch.cuda.cudart().cudaHostRegister(arr.ctypes.data, arr.nbytes, 1 | 2)  # portable | mapped
+            if int(rc) != 0:
+                raise RuntimeError(f"cudaHostRegister -> {rc}")
+            made = cls(arr, path, rank == 0)
+        except Exception as e:  # set-up only
+            err = e
+        ok = PeerImage._agree(made is not None, device, group) if world > 1 else made is not None
+        if not ok:
+            if made is not None:
+                made.close()
+            if err is not None and rank == 0:
+                import sys
+                print(f"[film_grain_b200.dist] shared host image unavailable: {err!r}", file=sys.stderr)
+            if rank == 0 and os.path.exists(path):
+                os.unlink(path)
+            return None
+        return made
+
+    def close(self):
+        import os
+
+        import torch
+        try:
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+        except Exception:
+            pass
+        if self._owner and os.path.exists(self._path):
+            os.unlink(self._path)

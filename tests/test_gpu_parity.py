@@ -229,25 +229,33 @@ def test_grainwise_matches_oracle(ctx, name, w, h, kw, path):
     assert 0.0 < ref.mean() < 1.0
 
 
-@pytest.mark.parametrize("algo", ["pixel", "grain"])
-def test_row_bands_equal_full_render(ctx, algo):
-    """multi-GPU contract: rendering disjoint row bands reproduces the full render bit for bit."""
+@pytest.mark.parametrize("algo,path,kw", [
+    ("pixel", 0, dict(radius=0.1, n_samples=8)), ("pixel", 1, dict(radius=0.1, n_samples=8)),
+    ("pixel", 2, dict(radius=0.1, n_samples=8)), ("pixel", 0, dict(radius=0.1, n_samples=6, cell_delta=0.7)),
+    ("pixel", 0, dict(radius=0.05, n_samples=6, zoom=2.5)),
+    ("grain", 0, dict(radius=0.6, n_samples=8, zoom=1.5)), ("grain", 1, dict(radius=0.6, n_samples=8, zoom=1.5)),
+], ids=["pixel-staged", "pixel-direct", "pixel-tiled", "pixel-coarse-cell", "pixel-zoom2.5", "grain-tiled", "grain-global-mask"])
+def test_row_bands_equal_full_render(ctx, algo, path, kw):
+    """multi-GPU contract: rendering disjoint row bands reproduces the full render bit for bit.  A band call
+    uploads only the input rows the band can read; conftest.py sets FG_B200_POISON, so every other row of
+    the device lambda buffer holds NaN during the call."""
     w, h = 72, 57
-    if algo == "pixel":
-        p = O.make_params(radius=0.1, n_samples=8, algo=O.ALGO_PIXEL)
-    else:
-        p = O.make_params(radius=0.6, n_samples=8, algo=O.ALGO_GRAIN, zoom=1.5)
+    p = O.make_params(algo=O.ALGO_PIXEL if algo == "pixel" else O.ALGO_GRAIN, **kw)
     d, off, off_in = O.derive_common(p, w, h)
     lam = lambda_from_u8(noise_u8(w, h, seed=9)[:, :, 2], d.inv_e_pi_r2)
     offs = off_in if algo == "pixel" else off
     render = ctx.render_pixelwise if algo == "pixel" else ctx.render_grainwise
-    full = render(fg_params_from(p, d), lam, offs)
+    full = render(fg_params_from(p, d, path=path), lam, offs)
     oh = d.output_height
     cuts = [0, oh // 3, oh // 3 + 1, (2 * oh) // 3, oh]
     banded = np.full_like(full, -1.0)
     for a, b in zip(cuts[:-1], cuts[1:]):
-        render(fg_params_from(p, d, rows=(a, b)), lam, offs, out=banded)
+        render(fg_params_from(p, d, rows=(a, b), path=path), lam, offs, out=banded)
+        st = ctx.stats()
+        assert st.h2d_bytes <= (h * w + 2 * p.n_samples) * 4
     assert np.array_equal(full, banded)
+    ref = O.render_pixelwise(lam, p, d, off_in) if algo == "pixel" else O.render_grainwise(lam, p, d, off)
+    assert np.array_equal(full, ref)
 
 
 def test_planes_batched_equals_sequential(ctx):
@@ -428,7 +436,7 @@ def test_multi_gpu_bands_into_peer_image_equal_single_gpu_render():
            "--master-port", "29533", os.path.join(root, "tools", "p2p_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "MISMATCH" not in r.stdout and r.stdout.count("bitwise equal") >= 6, r.stdout
+    assert "MISMATCH" not in r.stdout and r.stdout.count("bitwise equal") >= 9, r.stdout
 
 
 @pytest.mark.parametrize("algo", ["pixel", "grain"])

@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/p2p_check.py
 
 Every rank renders its row band (a) straight into GPU 0's peer-mapped image (PeerImage, each mode that
-can be set up) and (b) locally + NCCL gather; rank 0 renders the whole image alone and requires both
+can be set up), (b) locally + NCCL gather and (c) through the host-pointer call into one page-locked host image
+shared by all ranks; rank 0 renders the whole image alone and requires both
 assembled images to be bitwise identical to it.  Prints one line per check; exit code 1 on a mismatch.
 """
 import os
@@ -22,7 +23,7 @@ def main():
 
     import film_grain_b200 as fg
     from film_grain_b200 import host as H
-    from film_grain_b200.dist import PeerImage, band_rows, gather_bands
+    from film_grain_b200.dist import PeerImage, SharedHostImage, band_rows, gather_bands
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -78,6 +79,22 @@ def main():
                 same = bool(torch.equal(full.permute(1, 0, 2), ref))
                 ok &= same
                 print(f"{algo_name} {w}x{h} zoom {zoom}: NCCL gather: {'bitwise equal to the 1-GPU render' if same else 'MISMATCH'}", flush=True)
+        # host-pointer ABI call per rank, output = one page-locked host image shared by all ranks
+        shared = SharedHostImage.create((3, out_h, out_w), rank, world, dev)
+        if shared is None:
+            if rank == 0:
+                print(f"{algo_name} {w}x{h} zoom {zoom}: shared host image: NOT AVAILABLE", flush=True)
+        else:
+            shared.array[...] = -1.0
+            dist.barrier()
+            ctx.render_planes(blk, algo, [lam[c] for c in range(3)], offsets, [shared.array[c] for c in range(3)])
+            dist.barrier()
+            if rank == 0:
+                same = bool(np.array_equal(shared.array, ref.cpu().numpy()))
+                ok &= same
+                print(f"{algo_name} {w}x{h} zoom {zoom}: shared host image: {'bitwise equal to the 1-GPU render' if same else 'MISMATCH'}", flush=True)
+            dist.barrier()
+            shared.close()
         torch.cuda.synchronize()
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=dev)
