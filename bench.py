@@ -341,7 +341,8 @@ def main():
         e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
                "h2d_bytes_per_step": int(s.h2d_bytes), "d2h_bytes_per_step": int(s.d2h_bytes),
                "ms_per_step": e2e_ms, "h2d_ms": float(s.h2d_ms), "kernel_ms": float(s.kernel_ms), "d2h_ms": float(s.d2h_ms),
-               "call": "fg_render_planes (pinned host f32 lambda planes in, f32 planes out)"}
+               "call": "fg_render_planes (pinned host f32 lambda planes in, f32 planes out; the output planes are one page-locked "
+                       "block, which the kernels write in place over PCIe -- d2h_ms is the staged copy, 0 when in place)"}
         # the fused u8 entry point: 8-bit RGB over PCIe instead of f32 planes
         if planes == 3 and wl["algo"] == "pixel":
             pin_img = torch.from_numpy(np.ascontiguousarray(img)).pin_memory()
