@@ -121,7 +121,17 @@ int pixelwise_device(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
     const int band_rows = c.row_end - c.row_begin;
     uint32_t path = p->path;
-    if (path == FG_PATH_AUTO) path = FG_PATH_STAGED;
+    if (path == FG_PATH_AUTO) {
+        // The cell table costs ~ (6 / planes + 6.5) ps per Boolean-model cell of the band whatever N is (the
+        // first-draw bitmap is shared by the planes); evaluating from it costs ~6 ps per sample, regenerating
+        // the visited cells per sample (the reference's structure, k_pixelwise_direct) ~150 ps for a 3 x 3
+        // cell window.  Measured on a B200 (tools/path_probe.py, 4K plane): direct wins up to N = 8 at
+        // delta = 0.1 and up to N = 32 at delta = 0.05.  Few samples per cell -> regenerate.
+        const double per_axis = 2.0 * (double)p->rm / (double)p->delta + 1.0;
+        const double direct_ps = 150.0 * per_axis * per_axis / 9.0 - 6.0;
+        const double samples_per_cell = (double)p->n_samples * (double)p->zoom * (double)p->zoom * (double)p->delta * (double)p->delta;
+        path = (samples_per_cell * direct_ps < 6.0 / n_planes + 6.5) ? FG_PATH_DIRECT : FG_PATH_STAGED;
+    }
     if (path == FG_PATH_TILED || path == FG_PATH_STAGED) {
         int rc = tile_render(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, path);
         if (rc != 1) return rc; // 1 = "tiled path not applicable, use direct"

@@ -53,7 +53,7 @@ enum { FG_SEEDING_RAND_0_8 = 0, FG_SEEDING_RAND_0_9 = 1 };
 
 /* Which kernel family serves fg_render_pixelwise (diagnostics / tests; AUTO in production). */
 enum {
-    FG_PATH_AUTO = 0,   /* staged, falling back to tiled, falling back to direct */
+    FG_PATH_AUTO = 0,   /* staged (falling back to tiled, then direct); direct when there are too few samples per cell for the table to pay */
     FG_PATH_DIRECT = 1, /* per-sample regeneration (the reference's own structure) */
     FG_PATH_TILED = 2,  /* strip kernel generating its cell windows in shared memory */
     FG_PATH_STAGED = 3  /* cell table generated once per band in HBM, strip kernel loads windows */

@@ -230,9 +230,9 @@ def test_grainwise_matches_oracle(ctx, name, w, h, kw, path):
 
 
 @pytest.mark.parametrize("algo,path,kw", [
-    ("pixel", 0, dict(radius=0.1, n_samples=8)), ("pixel", 1, dict(radius=0.1, n_samples=8)),
-    ("pixel", 2, dict(radius=0.1, n_samples=8)), ("pixel", 0, dict(radius=0.1, n_samples=6, cell_delta=0.7)),
-    ("pixel", 0, dict(radius=0.05, n_samples=6, zoom=2.5)),
+    ("pixel", 3, dict(radius=0.1, n_samples=8)), ("pixel", 1, dict(radius=0.1, n_samples=8)),
+    ("pixel", 2, dict(radius=0.1, n_samples=8)), ("pixel", 3, dict(radius=0.1, n_samples=6, cell_delta=0.7)),
+    ("pixel", 3, dict(radius=0.05, n_samples=6, zoom=2.5)),
     ("grain", 0, dict(radius=0.6, n_samples=8, zoom=1.5)), ("grain", 1, dict(radius=0.6, n_samples=8, zoom=1.5)),
 ], ids=["pixel-staged", "pixel-direct", "pixel-tiled", "pixel-coarse-cell", "pixel-zoom2.5", "grain-tiled", "grain-global-mask"])
 def test_row_bands_equal_full_render(ctx, algo, path, kw):
@@ -471,3 +471,19 @@ def test_pinned_contiguous_output_planes_are_written_in_place(ctx, algo):
     for c in range(3):
         assert np.array_equal(outs[c][rows[0]:rows[1]], ref[c][rows[0]:rows[1]])
         assert np.all(outs[c][:rows[0]] == -7.0) and np.all(outs[c][rows[1]:] == -7.0)
+
+
+def test_auto_path_regenerates_when_samples_per_cell_are_few(ctx):
+    """FG_PATH_AUTO: the cell table costs the same whatever N is, so with few samples per cell the engine
+    regenerates per sample (k_pixelwise_direct, the reference's structure) and builds the table otherwise.
+    Same pixels either way."""
+    w, h = 160, 96
+    img = noise_u8(w, h, seed=4)
+    for n, expect_table in ((4, False), (64, True)):
+        p = O.make_params(radius=0.1, n_samples=n, algo=O.ALGO_PIXEL)
+        d, off, off_in = O.derive_common(p, w, h)
+        lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
+        got = ctx.render_pixelwise(fg_params_from(p, d, path=0), lam, off_in)
+        st = ctx.stats()
+        assert (st.tiles_total > 0) == expect_table, (n, st.tiles_total)
+        assert np.array_equal(got, O.render_pixelwise(lam, p, d, off_in))
