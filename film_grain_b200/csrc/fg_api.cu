@@ -163,7 +163,24 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     // bounded; fg_params.path == FG_PATH_DIRECT (tests) or an extreme zoom-out / radius selects the global-mask kernels.
     const double rmax = (double)p->rm * p->zoom;
     const double foot_rows = ((double)FG_GT_H + 2.0 + ((double)c.off_max_y - (double)c.off_min_y) + 2.0 * rmax) / p->zoom + 8.0;
-    const bool tiled = p->path != FG_PATH_DIRECT && foot_rows <= (double)FG_GT_MAXROWS && rmax < 4096.0;
+    bool tiled = p->path != FG_PATH_DIRECT && foot_rows <= (double)FG_GT_MAXROWS && rmax < 4096.0;
+    if (tiled && p->path == FG_PATH_AUTO) {
+        // Which rasteriser is faster (measured on a B200, C3 and the benchmarks/ sweep): the global-mask splat
+        // costs max(1.55 ps of instructions, 4.1 ps per covered pixel: one L2 atomic each) per (grain, sample)
+        // and spreads the grains evenly over the whole GPU; the tile kernel costs (1.45 + 0.25 per covered
+        // pixel) ps per pair, processes the margin grains of every tile again and keeps only as many SMs busy
+        // as there are tiles.  Small disks (few covered pixels per pair) or few tiles -> global mask.
+        const double r_out = (double)(p->radius_mean < p->rm ? p->radius_mean : p->rm) * p->zoom;
+        const double cover = 3.141592653589793 * r_out * r_out;
+        const double mx = std::fmax(std::fabs((double)c.off_min_x), std::fabs((double)c.off_max_x)) + rmax + 1.0;
+        const double my = std::fmax(std::fabs((double)c.off_min_y), std::fabs((double)c.off_max_y)) + rmax + 1.0;
+        const double halo = ((double)FG_GT_W + 2.0 * mx) * ((double)FG_GT_H + 2.0 * my) / ((double)FG_GT_W * FG_GT_H);
+        const double n_tiles = std::ceil((double)p->out_w / FG_GT_W) * std::ceil((double)(c.row_end - c.row_begin) / FG_GT_H);
+        // one CTA per SM: with fewer than ~3 waves of tiles the slowest tile (bright content holds many times
+        // the average number of grains) sets the time, while the global splat is balanced by construction
+        const double util = std::fmin(1.0, n_tiles / (3.0 * (double)ctx->sm_count));
+        tiled = std::fmax(1.55, 4.1 * cover) * util > (1.45 + 0.25 * cover) * halo;
+    }
     int rc;
     if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
     if (!tiled) {

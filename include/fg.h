@@ -51,7 +51,9 @@ enum { FG_ALGO_GRAIN = 1, FG_ALGO_PIXEL = 2 };            /* Algo (resolved), sr
  * fill; rand >= 0.9 forwards to xoshiro's SplitMix64 seeding. */
 enum { FG_SEEDING_RAND_0_8 = 0, FG_SEEDING_RAND_0_9 = 1 };
 
-/* Which kernel family serves fg_render_pixelwise (diagnostics / tests; AUTO in production). */
+/* Which kernel family serves fg_render_pixelwise (diagnostics / tests; AUTO in production).
+ * Grain-wise: FG_PATH_DIRECT = the global-mask rasteriser, FG_PATH_TILED / FG_PATH_STAGED = the
+ * shared-memory tile rasteriser, FG_PATH_AUTO = whichever the cost model expects to be faster. */
 enum {
     FG_PATH_AUTO = 0,   /* staged (falling back to tiled, then direct); direct when there are too few samples per cell for the table to pay */
     FG_PATH_DIRECT = 1, /* per-sample regeneration (the reference's own structure) */

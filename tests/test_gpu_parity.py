@@ -215,11 +215,11 @@ GRAIN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("path", [0, 1], ids=["tiled", "global_mask"])
+@pytest.mark.parametrize("path", [3, 1, 0], ids=["tiled", "global_mask", "auto"])
 @pytest.mark.parametrize("name,w,h,kw", GRAIN_CASES, ids=[c[0] for c in GRAIN_CASES])
 def test_grainwise_matches_oracle(ctx, name, w, h, kw, path):
-    """path 0: one CTA per output tile, coverage masks in shared memory (k_gw_tile); path 1
-    (FG_PATH_DIRECT): the global-mask kernels (k_gw_splat + k_gw_reduce)."""
+    """path 3 (FG_PATH_STAGED): one CTA per output tile, coverage masks in shared memory (k_gw_tile); path 1
+    (FG_PATH_DIRECT): the global-mask kernels (k_gw_splat + k_gw_reduce); path 0: the engine's choice."""
     p = O.make_params(algo=O.ALGO_GRAIN, **kw)
     d, off, off_in = O.derive_common(p, w, h)
     lam = lambda_from_u8(noise_u8(w, h, seed=5)[:, :, 1], d.inv_e_pi_r2)
@@ -233,7 +233,7 @@ def test_grainwise_matches_oracle(ctx, name, w, h, kw, path):
     ("pixel", 3, dict(radius=0.1, n_samples=8)), ("pixel", 1, dict(radius=0.1, n_samples=8)),
     ("pixel", 2, dict(radius=0.1, n_samples=8)), ("pixel", 3, dict(radius=0.1, n_samples=6, cell_delta=0.7)),
     ("pixel", 3, dict(radius=0.05, n_samples=6, zoom=2.5)),
-    ("grain", 0, dict(radius=0.6, n_samples=8, zoom=1.5)), ("grain", 1, dict(radius=0.6, n_samples=8, zoom=1.5)),
+    ("grain", 3, dict(radius=0.6, n_samples=8, zoom=1.5)), ("grain", 1, dict(radius=0.6, n_samples=8, zoom=1.5)),
 ], ids=["pixel-staged", "pixel-direct", "pixel-tiled", "pixel-coarse-cell", "pixel-zoom2.5", "grain-tiled", "grain-global-mask"])
 def test_row_bands_equal_full_render(ctx, algo, path, kw):
     """multi-GPU contract: rendering disjoint row bands reproduces the full render bit for bit.  A band call

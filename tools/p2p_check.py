@@ -45,6 +45,8 @@ def main():
         out_w, out_h = d.output_width, d.output_height
         rb, re = band_rows(out_h, rank, world)
         blk = H._band(d.block, (rb, re))
+        if algo_name == "grain":
+            blk.path = fg.FG_PATH_STAGED  # the shared-memory tile rasteriser (AUTO would pick the global mask for so few tiles)
         d_lam = torch.from_numpy(lam).to(dev)
         d_off = torch.from_numpy(np.ascontiguousarray(offsets)).to(dev)
         ref = None
