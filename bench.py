@@ -48,6 +48,8 @@ WORKLOADS = {
                desc="grain-wise luma 4096x4096 noise r=0.5 N=128"),
     "c4": dict(w=2048, h=2048, image="noise", planes=3, radius=0.05, n=64, zoom=4.0, algo="pixel",
                desc="pixel-wise RGB 2048x2048 zoom 4 (8192x8192 out) r=0.05 N=64"),
+    "c5g": dict(w=1024, h=1024, image="noise", planes=1, radius=0.12, n=1024, zoom=1.0, algo="grain",
+                desc="grain-wise luma 1024x1024 r=0.12 N=1024 (high-sample sweep point, grain-wise forced)"),
     "c5": dict(w=1024, h=1024, image="noise", planes=1, radius=0.12, n=1024, zoom=1.0, algo="pixel",
                desc="pixel-wise luma 1024x1024 r=0.12 N=1024 (high-sample sweep point)"),
 }

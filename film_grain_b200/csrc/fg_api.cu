@@ -218,12 +218,15 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
                 uint64_t want_blocks = (total + 255) / 256;
                 const uint64_t max_blocks = (uint64_t)ctx->sm_count * 64;
                 unsigned sblocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
-                if ((size_t)p->out_w * p->out_h * lanes32 < ((size_t)1 << 32)) // word indices relative to row 0 fit 32 bits
-                    k_gw_splat<uint32_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
-                                                                           (uint32_t*)ctx->bits.p, lanes32, c);
-                else
-                    k_gw_splat<size_t><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets,
-                                                                         (uint32_t*)ctx->bits.p, lanes32, c);
+                const bool idx32 = (size_t)p->out_w * p->out_h * lanes32 < ((size_t)1 << 32); // word indices relative to row 0 fit 32 bits
+                static const bool sparse_env = !(std::getenv("FG_B200_GW_SPARSE") && std::atoi(std::getenv("FG_B200_GW_SPARSE")) == 0); // experiments
+                const bool sparse = sparse_env && 2.0 * rmax < 0.6 && p->out_w < (1u << 21) && p->out_h < (1u << 21);                          // at most ~1/3 of the boxes are non-empty
+#define FG_SPLAT(IDX, SP)                                                                                                    \
+    k_gw_splat<IDX, SP><<<sblocks, 256, 0, ctx->stream>>>((const GrainRec*)ctx->grains.p, d_total, (const float2*)d_offsets, \
+                                                          (uint32_t*)ctx->bits.p, lanes32, c)
+                if (idx32) { if (sparse) FG_SPLAT(uint32_t, true); else FG_SPLAT(uint32_t, false); }
+                else { if (sparse) FG_SPLAT(size_t, true); else FG_SPLAT(size_t, false); }
+#undef FG_SPLAT
                 FG_CUDA(ctx, cudaGetLastError());
                 ctx->stats.launches += 1;
             }

@@ -227,7 +227,66 @@ __device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn
 // Lanes of a warp hold consecutive grains of the same input pixels, so their reductions land on
 // neighbouring mask words.  IDX = uint32_t when the whole image's mask has fewer than 2^32 words.
 #define FG_GW_OFF_CHUNK 2048 // sample offsets staged in shared memory per pass (16 KB), a multiple of 32
-template <typename IDX>
+// One (grain, sample) pair of the global-mask rasteriser: bounds() clipped to the image / row band, then
+// the pixel tests.  `t` = (tx, ty).  Returns false when the box is empty (nothing was written).
+template <typename IDX, bool TEST_ONLY>
+__device__ __forceinline__ bool gw_pair_global(f32x2 t, f32x2 rr, float R2, int last_x, int lo_y, int hi_y, uint32_t* bw,
+                                               IDX xstep, IDX ystep, uint32_t bit) {
+    const f32x2 half2 = f2_make(0.5f, 0.5f), one2 = f2_make(1.0f, 1.0f);
+    float lx, ly, hx, hy;
+    f2_split(f2_sub(f2_sub(t, rr), half2), lx, ly);
+    f2_split(f2_sub(f2_add(t, rr), half2), hx, hy);
+    const int x_min = max(__float2int_ru(lx), 0), x_max = min(__float2int_rd(hx), last_x);
+    const int y_min = max(__float2int_ru(ly), lo_y), y_max = min(__float2int_rd(hy), hi_y);
+    const int wx = x_max - x_min, wy = y_max - y_min;
+    if ((wx | wy) < 0) return false; // empty in x or y
+    if (TEST_ONLY) return true;
+    const IDX i00 = (IDX)y_min * ystep + (IDX)x_min * xstep;
+    const f32x2 f0 = f2_add(f2_make((float)x_min, (float)y_min), half2); // pixel centre (ox + 0.5, oy + 0.5)
+    float sx0, sy0;
+    f2_split(f2_mul(f2_sub(f0, t), f2_sub(f0, t)), sx0, sy0);
+    if ((wx | wy) == 0) { // one pixel
+        if (__fadd_rn(sx0, sy0) <= R2) atomicOr(bw + i00, bit);
+        return true;
+    }
+    if (wx <= 1 && wy <= 1) {
+        // (ox + 1) + 0.5 == (ox + 0.5) + 1 exactly: |ox| < 2^22 after clipping to the image
+        const f32x2 f1 = f2_add(f0, one2);
+        float sx1, sy1;
+        f2_split(f2_mul(f2_sub(f1, t), f2_sub(f1, t)), sx1, sy1);
+        const bool x1 = wx > 0, y1 = wy > 0;
+        if (__fadd_rn(sx0, sy0) <= R2) atomicOr(bw + i00, bit);
+        if (x1 && __fadd_rn(sx1, sy0) <= R2) atomicOr(bw + (i00 + xstep), bit);
+        if (y1 && __fadd_rn(sx0, sy1) <= R2) atomicOr(bw + (i00 + ystep), bit);
+        if (x1 && y1 && __fadd_rn(sx1, sy1) <= R2) atomicOr(bw + (i00 + ystep + xstep), bit);
+        return true;
+    }
+    float tx, ty;
+    f2_split(t, tx, ty);
+    uint32_t* p00 = bw + i00;
+    for (int oy = y_min; oy <= y_max; ++oy, p00 += ystep) {
+        const float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
+        const float dy_sq = __fmul_rn(dy, dy);
+        if (dy_sq > R2) continue;
+        uint32_t* p = p00;
+        for (int ox = x_min; ox <= x_max; ++ox, p += xstep) {
+            const float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
+            if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= R2) atomicOr(p, bit);
+        }
+    }
+    return true;
+}
+
+// SPARSE: disks much smaller than a pixel (2R << 1) leave most boxes empty, but in a warp some lane almost
+// always has a non-empty one, so the warp would walk the box arithmetic (four F2I on the quarter-rate XU pipe:
+// the measured bound of the dense loop on such inputs) and the pixel tests for nearly every sample.  The
+// sparse variant first runs a cheap NECESSARY condition for "the box holds a pixel centre" on the 32 samples
+// of a mask word -- the distance from tx - 0.5 to the nearest integer (magic-number rounding, FMA pipe only)
+// is at most R plus a bound on the f32 rounding of the reference's box arithmetic, in x and in y -- and keeps
+// the survivors as a bit mask per lane; then it drains the masks through the exact code.  A pair that fails
+// the condition has an empty box (so the reference writes nothing for it); survivors run the same arithmetic
+// as in the dense loop.  Valid for image coordinates below 2^21 (checked by the host).
+template <typename IDX, bool SPARSE>
 __global__ void __launch_bounds__(256) k_gw_splat(const GrainRec* __restrict__ grains, const uint64_t* __restrict__ n_grains_ptr,
                                                    const float2* __restrict__ offsets, uint32_t* __restrict__ bits,
                                                    uint32_t lanes32, RenderConsts c) {
@@ -235,7 +294,9 @@ __global__ void __launch_bounds__(256) k_gw_splat(const GrainRec* __restrict__ g
     const uint64_t total = *n_grains_ptr;
     const int last_x = c.out_w - 1, lo_y = c.row_begin, hi_y = c.row_end - 1;
     const IDX xstep = (IDX)lanes32, ystep = (IDX)c.out_w * (IDX)lanes32;
-    const f32x2 half2 = f2_make(0.5f, 0.5f), one2 = f2_make(1.0f, 1.0f);
+    const f32x2 half2 = f2_make(0.5f, 0.5f), magic2 = f2_make(12582912.0f, 12582912.0f); // 1.5 * 2^23
+    // 8 ulp of the largest coordinate that can still reach the image (box arithmetic: 3 roundings, u: 1, margin x2)
+    const float eps_box = (float)(max(c.out_w, c.out_h) + 64) * 9.5367431640625e-7f; // * 2^-20
     for (uint32_t k0 = 0; k0 < c.n; k0 += FG_GW_OFF_CHUNK) {
         const uint32_t kn = min((uint32_t)FG_GW_OFF_CHUNK, c.n - k0);
         if (k0) __syncthreads();
@@ -248,55 +309,32 @@ __global__ void __launch_bounds__(256) k_gw_splat(const GrainRec* __restrict__ g
             const float R = rv.z, R2 = rv.w;
             if (!(R > 0.0f)) continue;
             const f32x2 ctr = f2_make(rv.x, rv.y), rr = f2_make(R, R);
+            // |(tx - 0.5) - nearest integer| <= R + eps is necessary for a pixel centre in [(tx - R) - 0.5, (tx + R) - 0.5]:
+            // eps covers the roundings of those two expressions and of tx - 0.5 (each <= 1 ulp of a coordinate < 2^21 + reach)
+            const float Re = __fadd_rn(R, eps_box);
             float2 o = s_off[0];
             for (uint32_t kw = 0; kw < kn; kw += 32) {
                 uint32_t* const bw = bits0 + (IDX)(kw >> 5);
                 const uint32_t ke = min(32u, kn - kw);
+                uint32_t surv = 0;
 #pragma unroll 4
                 for (uint32_t kb = 0; kb < ke; ++kb) {
                     const f32x2 t = f2_add(ctr, f2_make(o.x, o.y)); // (tx, ty) = (cx*zoom + ox, cy*zoom + oy)
                     o = s_off[kw + kb + 1];                         // next sample's offset (entry kn is padding)
-                    float lx, ly, hx, hy;
-                    f2_split(f2_sub(f2_sub(t, rr), half2), lx, ly);
-                    f2_split(f2_sub(f2_add(t, rr), half2), hx, hy);
-                    const int x_min = max(__float2int_ru(lx), 0), x_max = min(__float2int_rd(hx), last_x);
-                    const int y_min = max(__float2int_ru(ly), lo_y), y_max = min(__float2int_rd(hy), hi_y);
-                    const int wx = x_max - x_min, wy = y_max - y_min;
-                    if ((wx | wy) < 0) continue; // empty in x or y
-                    const uint32_t bit = 1u << kb;
-                    const IDX i00 = (IDX)y_min * ystep + (IDX)x_min * xstep;
-                    const f32x2 f0 = f2_add(f2_make((float)x_min, (float)y_min), half2); // pixel centre (ox + 0.5, oy + 0.5)
-                    float sx0, sy0;
-                    f2_split(f2_mul(f2_sub(f0, t), f2_sub(f0, t)), sx0, sy0);
-                    if ((wx | wy) == 0) { // one pixel
-                        if (__fadd_rn(sx0, sy0) <= R2) atomicOr(bw + i00, bit);
-                        continue;
+                    if (SPARSE) {
+                        const f32x2 u = f2_sub(t, half2);
+                        float dx, dy;
+                        f2_split(f2_sub(u, f2_sub(f2_add(u, magic2), magic2)), dx, dy); // u - rint(u), exact for |u| < 2^22
+                        surv |= (fabsf(dx) <= Re && fabsf(dy) <= Re) ? (1u << kb) : 0u;
+                    } else {
+                        gw_pair_global<IDX, false>(t, rr, R2, last_x, lo_y, hi_y, bw, xstep, ystep, 1u << kb);
                     }
-                    if (wx <= 1 && wy <= 1) {
-                        // (ox + 1) + 0.5 == (ox + 0.5) + 1 exactly: |ox| < 2^22 after clipping to the image
-                        const f32x2 f1 = f2_add(f0, one2);
-                        float sx1, sy1;
-                        f2_split(f2_mul(f2_sub(f1, t), f2_sub(f1, t)), sx1, sy1);
-                        const bool x1 = wx > 0, y1 = wy > 0;
-                        if (__fadd_rn(sx0, sy0) <= R2) atomicOr(bw + i00, bit);
-                        if (x1 && __fadd_rn(sx1, sy0) <= R2) atomicOr(bw + (i00 + xstep), bit);
-                        if (y1 && __fadd_rn(sx0, sy1) <= R2) atomicOr(bw + (i00 + ystep), bit);
-                        if (x1 && y1 && __fadd_rn(sx1, sy1) <= R2) atomicOr(bw + (i00 + ystep + xstep), bit);
-                        continue;
-                    }
-                    float tx, ty;
-                    f2_split(t, tx, ty);
-                    uint32_t* p00 = bw + i00;
-                    for (int oy = y_min; oy <= y_max; ++oy, p00 += ystep) {
-                        const float dy = __fsub_rn(__fadd_rn((float)oy, 0.5f), ty);
-                        const float dy_sq = __fmul_rn(dy, dy);
-                        if (dy_sq > R2) continue;
-                        uint32_t* p = p00;
-                        for (int ox = x_min; ox <= x_max; ++ox, p += xstep) {
-                            const float dx = __fsub_rn(__fadd_rn((float)ox, 0.5f), tx);
-                            if (__fadd_rn(__fmul_rn(dx, dx), dy_sq) <= R2) atomicOr(p, bit);
-                        }
-                    }
+                }
+                while (SPARSE && surv) {
+                    const uint32_t kb = (uint32_t)__ffs(surv) - 1u;
+                    surv &= surv - 1u;
+                    const float2 ok = s_off[kw + kb];
+                    gw_pair_global<IDX, false>(f2_add(ctr, f2_make(ok.x, ok.y)), rr, R2, last_x, lo_y, hi_y, bw, xstep, ystep, 1u << kb);
                 }
             }
         }

@@ -210,6 +210,9 @@ GRAIN_CASES = [
     ("r0.4_zoom1.5_box2x2", 48, 40, dict(radius=0.4, n_samples=40, zoom=1.5)),  # R = 0.6: boxes of 1-2 pixels per axis
     ("r0.7_box2x2", 40, 36, dict(radius=0.7, n_samples=33)),
     ("r0.5_N2100_two_offset_passes", 20, 16, dict(radius=0.5, n_samples=2100)),  # > 2048 offsets: second shared-memory pass
+    ("r0.1_N70_small_disks", 48, 40, dict(radius=0.1, n_samples=70)),             # 2R = 0.2: the sparse (survivor mask) splat
+    ("r0.12_zoom2_small_disks", 40, 30, dict(radius=0.12, n_samples=33, zoom=2.0)),
+    ("r0.1_wide_4096_small_disks", 4096, 6, dict(radius=0.1, n_samples=24)),      # coordinates up to 4096: f32 ulp 4.9e-4 against the sparse prefilter's slack
     ("r0.5_multi_tile", 300, 150, dict(radius=0.5, n_samples=8)),                 # 3 x 3 output tiles of 128 x 64
     ("r0.3_zoom2_multi_tile", 100, 70, dict(radius=0.3, n_samples=36, zoom=2.0)),
 ]
