@@ -445,17 +445,19 @@ def main():
             kernel_ms = (strip_total_ms / args.steps) if strip_total_ms > 0 else ms_per_step
             tab_ms = table_total_ms / args.steps
             achieved = ao["ops_eval"] / strip_launches / (kernel_ms * 1e-3) / 1e12
-            traffic = None
+            traffic, issue_active = None, None
             prof = os.path.join(ROOT, "profiles", "strip_dram_bytes.json")
             if os.path.exists(prof):
                 try:
-                    traffic = json.load(open(prof)).get(args.workload)
+                    pj = json.load(open(prof))
+                    traffic, issue_active = pj.get(args.workload), pj.get(args.workload + "_issue_active")
                 except Exception:
                     traffic = None
             io_bytes = planes * (wl["w"] * wl["h"] * 16 + out_w * out_h * 4)  # thr+e planes in, f32 plane out
             peak = issue["ffma"] / 1e3 * world  # aggregate over the GPUs that shared the launch's work
             roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
                     "frac": achieved / peak, "traffic": traffic,
+                    "issue_slots_filled": issue_active,  # ncu smsp__issue_active of the committed capture (executed, not algorithmic, instructions)
                     "kernel": "k_pixelwise_strip", "kernel_ms": kernel_ms, "share_of_step": kernel_ms / ms_per_step,
                     "launches_per_step": strip_launches,
                     "table": {"kernels": "k_thresholds + k_first_draw_bitmap + k_row_expect + k_row_bases + k_gen_rows",
