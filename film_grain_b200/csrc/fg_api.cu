@@ -183,13 +183,9 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     }
     int rc;
     if ((rc = ensure(ctx, ctx->misc, 64))) return rc;
-    if (!tiled) {
-        if ((rc = ensure(ctx, ctx->bits, band_pix * lanes32 * sizeof(uint32_t)))) return rc;
-        FG_CUDA(ctx, cudaMemsetAsync(ctx->bits.p, 0, band_pix * lanes32 * sizeof(uint32_t), ctx->stream));
-    }
     uint64_t* d_total = (uint64_t*)ctx->misc.p;
     uint64_t total = 0;
-    bool ev4 = false;
+    bool ev4 = false, bits_ready = false;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream)); // ev[6]..ev[4]: grain generation, ev[4]..ev[5]: rasterisation
     if (npix_in > 0) {
         if ((rc = ensure(ctx, ctx->counts, npix_in * sizeof(uint32_t)))) return rc;
@@ -207,6 +203,7 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
         FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->stats.launches += 4;
         if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+        if (total >> 32) tiled = false; // the tile kernel indexes a tile's grains with 32 bits
         if (total > 0) {
             if ((rc = ensure(ctx, ctx->grains, total * sizeof(GrainRec)))) return rc;
             k_gw_fill<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (const uint64_t*)ctx->scan_out.p, (GrainRec*)ctx->grains.p, c);
@@ -215,6 +212,9 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
             FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
             ev4 = true;
             if (!tiled) {
+                if ((rc = ensure(ctx, ctx->bits, band_pix * lanes32 * sizeof(uint32_t)))) return rc;
+                FG_CUDA(ctx, cudaMemsetAsync(ctx->bits.p, 0, band_pix * lanes32 * sizeof(uint32_t), ctx->stream));
+                bits_ready = true;
                 uint64_t want_blocks = (total + 255) / 256;
                 const uint64_t max_blocks = (uint64_t)ctx->sm_count * 64;
                 unsigned sblocks = (unsigned)(want_blocks < max_blocks ? want_blocks : max_blocks);
@@ -249,6 +249,10 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
         }
         FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
         return FG_OK;
+    }
+    if (!bits_ready) { // no grains at all: an empty mask
+        if ((rc = ensure(ctx, ctx->bits, band_pix * lanes32 * sizeof(uint32_t)))) return rc;
+        FG_CUDA(ctx, cudaMemsetAsync(ctx->bits.p, 0, band_pix * lanes32 * sizeof(uint32_t), ctx->stream));
     }
     k_gw_reduce<<<(unsigned)((band_pix + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->bits.p, lanes32, d_out, c);
     FG_CUDA(ctx, cudaGetLastError());
