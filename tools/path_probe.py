@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small-N probe (run on a GPU box): device-resident pixel-wise render of a 4K luma noise plane at N = 1..64
-through each kernel family (FG_PATH_DIRECT / TILED / STAGED); prints ms per render.  Used to place the
+through each kernel family (FG_PATH_DIRECT / TILED / STAGED) and through FG_PATH_AUTO; prints ms per render.  Used to place the
 crossover below which the cell table (whose cost does not depend on N) stops paying."""
 import os
 import sys
@@ -31,7 +31,7 @@ def main():
             d_off = torch.from_numpy(np.ascontiguousarray(d.offsets_input)).to(dev)
             d_out = torch.zeros((d.output_height, d.output_width), dtype=torch.float32, device=dev)
             row = []
-            for path in (fg.FG_PATH_DIRECT, fg.FG_PATH_TILED, fg.FG_PATH_STAGED):
+            for path in (fg.FG_PATH_DIRECT, fg.FG_PATH_TILED, fg.FG_PATH_STAGED, fg.FG_PATH_AUTO):
                 blk = H._band(d.block, None)
                 blk.path = path
                 with torch.cuda.stream(stream):
@@ -44,7 +44,7 @@ def main():
                     b.record(stream)
                     stream.synchronize()
                 row.append(a.elapsed_time(b) / 3)
-            print(f"r={radius} N={n:3d}  direct {row[0]:8.2f} ms   tiled {row[1]:8.2f} ms   staged {row[2]:8.2f} ms", flush=True)
+            print(f"r={radius} N={n:3d}  direct {row[0]:8.2f} ms   tiled {row[1]:8.2f} ms   staged {row[2]:8.2f} ms   auto {row[3]:8.2f} ms", flush=True)
     torch.cuda.synchronize()
     os._exit(0)
 
