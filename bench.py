@@ -172,6 +172,15 @@ def algorithmic_ops(wl: dict, d_block, off_in: np.ndarray, n_cell: float, n_test
     return dict(ops=ops, ops_eval=ops_eval, ops_gen=ops_gen, S=S, G=G, ops_per_eval=ops / S)
 
 
+def host_threads() -> int:
+    """All the host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would silently turn the CPU arm into a single-thread run: the thread count is passed explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust crate cannot be
     built in this image (no cargo/rustc), so this is the oracle port (kind 'port'), all host threads."""
@@ -180,10 +189,10 @@ def run_reference(args, wl, rank, world):
     img = synth_image(wl["image"], wl["w"], wl["h"])
     per_step = max(2.0, min(12.0, 90.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        oracle_sample(wl, img, per_step / 4)
+        oracle_sample(wl, img, per_step / 4, host_threads())
     rates, last = [], None
     for _ in range(args.steps):
-        last = oracle_sample(wl, img, per_step)
+        last = oracle_sample(wl, img, per_step, host_threads())
         rates.append(last["rate"])
     rate = float(np.mean(rates))
     planes = wl["planes"]
@@ -236,6 +245,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    # stdout carries exactly one JSON line: whatever native libraries print while the job runs (NCCL's version
+    # banner, ...) goes to stderr; the descriptor is restored right before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -433,7 +447,7 @@ def main():
         cpu, roof = None, None
         n_cell, n_test = 6.6, 1.6
         if world == 1 and not args.no_cpu:
-            sm = oracle_sample(wl, img, args.cpu_seconds)
+            sm = oracle_sample(wl, img, args.cpu_seconds, host_threads())
             n_cell, n_test = (sm["n_cell"], sm["n_test"]) if wl["algo"] == "pixel" else (n_cell, n_test)
             cpu = {"value": sm["rate"] / planes / 1e6, "unit": "Mpixel*samples/s", "cores": sm["threads"], "kind": "port",
                    "sample": sm["sample"], "seconds": sm["seconds"]}
@@ -512,6 +526,8 @@ def main():
                        "tiles": tiles_total, "tiles_fallback": tiles_fb},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line, default=float), flush=True)
     # teardown: torch's device and pinned-host allocators record events on every stream a block was
     # used on -- including the engine's stream -- when blocks are released at interpreter exit, i.e.
