@@ -187,7 +187,7 @@ def run_reference(args, wl, rank, world):
     if rank != 0:
         return
     img = synth_image(wl["image"], wl["w"], wl["h"])
-    per_step = max(2.0, min(12.0, 90.0 / max(1, args.steps + args.warmup)))
+    per_step = args.cpu_seconds if args.cpu_seconds else max(2.0, min(12.0, 90.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         oracle_sample(wl, img, per_step / 4, host_threads())
     rates, last = [], None
@@ -220,7 +220,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=None,
+                    help="budget of the CPU sample (default: 12 s for cpu_baseline; ~90 s over all steps of --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--bands", default="auto", choices=["auto", "peer", "gather"],
                     help="N > 1: how the finished bands reach GPU 0 (peer = the kernels store straight into GPU 0's image "
@@ -447,7 +448,7 @@ def main():
         cpu, roof = None, None
         n_cell, n_test = 6.6, 1.6
         if world == 1 and not args.no_cpu:
-            sm = oracle_sample(wl, img, args.cpu_seconds, host_threads())
+            sm = oracle_sample(wl, img, args.cpu_seconds or 12.0, host_threads())
             n_cell, n_test = (sm["n_cell"], sm["n_test"]) if wl["algo"] == "pixel" else (n_cell, n_test)
             cpu = {"value": sm["rate"] / planes / 1e6, "unit": "Mpixel*samples/s", "cores": sm["threads"], "kind": "port",
                    "sample": sm["sample"], "seconds": sm["seconds"]}
