@@ -490,3 +490,35 @@ def test_auto_path_regenerates_when_samples_per_cell_are_few(ctx):
         st = ctx.stats()
         assert (st.tiles_total > 0) == expect_table, (n, st.tiles_total)
         assert np.array_equal(got, O.render_pixelwise(lam, p, d, off_in))
+
+
+def test_full_size_config5_both_algorithms(ctx):
+    """BASELINE.json configs[4] geometry (luma 1024^2, r = 0.12: delta = 1/9 with rm = 0.12, i.e. 3-4 cells per
+    axis).  Pixel-wise at N = 1024 (four sample chunks): a 24-row band, staged == tiled == direct, and == the
+    oracle on 3 rows.  Grain-wise at N = 256 (sub-pixel disks): the tile rasteriser, the dense global-mask
+    rasteriser (sparse instance) and the engine's own pick agree bit for bit on the whole image, whose mean
+    reproduces the input's (the Boolean-model identity E[pixel] = u)."""
+    w = h = 1024
+    img = noise_u8(w, h)[:, :, 0]
+    p = O.make_params(radius=0.12, n_samples=1024, algo=O.ALGO_PIXEL, seed=5489)
+    d, off, off_in = O.derive_common(p, w, h)
+    assert abs(d.delta - 1.0 / 9.0) < 1e-7
+    lam = lambda_from_u8(img, d.inv_e_pi_r2)
+    a, b = 500, 524
+    outs = {}
+    for path in (1, 2, 3):
+        outs[path] = np.zeros((h, w), np.float32)
+        ctx.render_pixelwise(fg_params_from(p, d, path=path, rows=(a, b)), lam, off_in, out=outs[path])
+    assert np.array_equal(outs[2][a:b], outs[1][a:b]) and np.array_equal(outs[3][a:b], outs[1][a:b])
+    ref = O.render_pixelwise(lam, p, d, off_in, a, a + 3)
+    assert np.array_equal(ref[a:a + 3], outs[3][a:a + 3])
+    assert 0.3 < outs[3][a:b].mean() < 0.7
+
+    pg = O.make_params(radius=0.12, n_samples=256, algo=O.ALGO_GRAIN, seed=5489)
+    dg, offg, _ = O.derive_common(pg, w, h)
+    lamg = lambda_from_u8(img, dg.inv_e_pi_r2)
+    tile = ctx.render_grainwise(fg_params_from(pg, dg, path=3), lamg, offg)
+    glob = ctx.render_grainwise(fg_params_from(pg, dg, path=1), lamg, offg)
+    auto = ctx.render_grainwise(fg_params_from(pg, dg, path=0), lamg, offg)
+    assert np.array_equal(tile, glob) and np.array_equal(auto, glob)
+    assert abs(float(glob.mean()) - float(img.mean()) / 255.0) < 0.03  # E[pixel] ~ u (Boolean-model identity; exact for constant input)
