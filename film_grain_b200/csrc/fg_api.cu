@@ -190,8 +190,9 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     if (npix_in > 0) {
         if ((rc = ensure(ctx, ctx->counts, npix_in * sizeof(uint32_t)))) return rc;
         if ((rc = ensure(ctx, ctx->scan_out, npix_in * sizeof(uint64_t)))) return rc;
+        if ((rc = ensure(ctx, ctx->gw_states, npix_in * sizeof(ulonglong4)))) return rc;
         const unsigned blocks = (unsigned)((npix_in + 255) / 256);
-        k_gw_count<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (uint32_t*)ctx->counts.p, c);
+        k_gw_count<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (uint32_t*)ctx->counts.p, (ulonglong4*)ctx->gw_states.p, c);
         FG_CUDA(ctx, cudaGetLastError());
         cub::TransformInputIterator<uint64_t, ToU64, const uint32_t*> it((const uint32_t*)ctx->counts.p, ToU64());
         size_t tmp_bytes = 0;
@@ -206,7 +207,8 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
         if (total >> 32) tiled = false; // the tile kernel indexes a tile's grains with 32 bits
         if (total > 0) {
             if ((rc = ensure(ctx, ctx->grains, total * sizeof(GrainRec)))) return rc;
-            k_gw_fill<<<blocks, 256, 0, ctx->stream>>>(d_lambda, iy0, iy1, (const uint64_t*)ctx->scan_out.p, (GrainRec*)ctx->grains.p, c);
+            k_gw_fill<<<blocks, 256, 0, ctx->stream>>>(iy0, iy1, (const uint32_t*)ctx->counts.p, (const ulonglong4*)ctx->gw_states.p,
+                                                       (const uint64_t*)ctx->scan_out.p, (GrainRec*)ctx->grains.p, c);
             FG_CUDA(ctx, cudaGetLastError());
             ctx->stats.launches += 1;
             FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -444,7 +446,7 @@ void fg_context_destroy(fg_ctx* ctx) {
         ScopedDevice dev(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         for (DevBuf* b : {&ctx->lambda, &ctx->out, &ctx->offsets, &ctx->bits, &ctx->counts, &ctx->scan_out, &ctx->scan_tmp,
-                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->bitmap, &ctx->rowinfo, &ctx->ptab, &ctx->gtab, &ctx->fbtotal, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut})
+                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->bitmap, &ctx->rowinfo, &ctx->ptab, &ctx->gtab, &ctx->fbtotal, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut, &ctx->gw_states})
             release(*b);
         for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -34,7 +34,7 @@ struct fg_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     // pools
-    DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, bitmap, rowinfo, ptab, gtab, fbtotal, rgb_in, rgb_out, chroma, lut;
+    DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, bitmap, rowinfo, ptab, gtab, fbtotal, rgb_in, rgb_out, chroma, lut, gw_states;
     bool tables_ready = false;
     uint32_t fb_count_host = 0; // tiled path: fallback-list length of the last render (valid after a stream sync)
     bool fb_pending = false;

@@ -155,13 +155,13 @@ __global__ void k_dump_cells(const int2* __restrict__ ij, const float* __restric
 }
 
 // ---- grain-wise: grain-parallel rasteriser (src/grainwise.rs:12-124) ---------------------
-// Pass 1: Poisson count per input pixel of rows [iy0, iy1).  Pass 2 (after an exclusive
-// scan) regenerates the same pixels and writes their grains; both passes draw from the
-// pixel's own RNG stream, so the realisation does not depend on the traversal order.
+// Pass 1: Poisson count per input pixel of rows [iy0, iy1), keeping the pixel's generator state.  Pass 2
+// (after an exclusive scan) continues each pixel's own RNG stream and writes its grains in pixel order,
+// so the realisation does not depend on the traversal order.
 struct GrainRec { float cxz, cyz, radius_out, radius_sq; }; // centre in OUTPUT px (cx*zoom), R, R^2
 
 __global__ void __launch_bounds__(256) k_gw_count(const float* __restrict__ lambda, int iy0, int iy1,
-                                                   uint32_t* __restrict__ counts, RenderConsts c) {
+                                                   uint32_t* __restrict__ counts, ulonglong4* __restrict__ states, RenderConsts c) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t npix = (size_t)(iy1 - iy0) * c.in_w;
     if (t >= npix) return;
@@ -172,22 +172,25 @@ __global__ void __launch_bounds__(256) k_gw_count(const float* __restrict__ lamb
         Xoshiro rng;
         seed_small_rng(rng, mix3_row(mix3_col(c.seed_pixel, x), y), c.seeding);
         q = poisson_f64(rng, (double)lam);
+        // the generator right after the Poisson draw: the fill pass continues from here instead of
+        // seeding and sampling the pixel a second time
+        if (q) states[t] = make_ulonglong4(rng.s0, rng.s1, rng.s2, rng.s3);
     }
     counts[t] = q;
 }
 
-__global__ void __launch_bounds__(256) k_gw_fill(const float* __restrict__ lambda, int iy0, int iy1,
-                                                  const uint64_t* __restrict__ offsets_excl,
+__global__ void __launch_bounds__(256) k_gw_fill(int iy0, int iy1, const uint32_t* __restrict__ counts,
+                                                  const ulonglong4* __restrict__ states, const uint64_t* __restrict__ offsets_excl,
                                                   GrainRec* __restrict__ grains, RenderConsts c) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t npix = (size_t)(iy1 - iy0) * c.in_w;
     if (t >= npix) return;
+    const uint32_t q = counts[t];
+    if (!q) return;
     int x = (int)(t % c.in_w), y = iy0 + (int)(t / c.in_w);
-    float lam = __ldg(lambda + (size_t)y * c.in_w + x);
-    if (!(lam > 0.0f)) return;
+    const ulonglong4 st = states[t];
     Xoshiro rng;
-    seed_small_rng(rng, mix3_row(mix3_col(c.seed_pixel, x), y), c.seeding);
-    uint32_t q = poisson_f64(rng, (double)lam);
+    rng.s0 = st.x; rng.s1 = st.y; rng.s2 = st.z; rng.s3 = st.w;
     GrainRec* dst = grains + offsets_excl[t];
     for (uint32_t g = 0; g < q; ++g) {
         float cx = __fadd_rn((float)x, uniform_f32(rng, c.uscale_unit));
