@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ la
 // and per strip window inside the strip kernel.  grid (ceil(rows/FG_BM_ROWS), ceil(cols/256)), block 256,
 // one thread per cell column; each warp
 // stores one aligned 32-bit word per plane.
+#ifndef FG_BM_ROWS
 #define FG_BM_ROWS 16 // cell rows per thread in k_first_draw_bitmap (amortises the column half of the hash)
+#endif
 template <int SEEDING, int NP> // compile-time seeding variant and plane count (NP = 0: run-time n_planes)
 __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __restrict__ thr_planes, size_t in_stride,
                                                             int n_planes, uint32_t* __restrict__ bm, size_t bm_plane_words,
