@@ -58,3 +58,10 @@ def test_gather_bands_gloo_world2(h):
     for p in procs:
         p.join(timeout=60)
     assert all(res)
+
+
+def test_peer_image_is_not_used_for_a_single_rank():
+    """world == 1: no peer mapping, the engine renders into its own buffer (and importing the module needs no GPU)."""
+    import torch
+    from film_grain_b200.dist import PeerImage
+    assert PeerImage.create((3, 8, 8), torch.float32, "cpu", 0, 1) is None
