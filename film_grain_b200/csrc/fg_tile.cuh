@@ -868,10 +868,11 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                                     if (d2 <= r2) { dminB = d2; break; }
                                 } while (++u < nB);
                             }
-                            offA += PS2;
-                            if (offA >= Ps + RHPS2) offA = Ps;
-                            offB += PS2;
-                            if (offB >= Ps + RHPS2) offB = Ps;
+                            // advance only inside the sample's own rows: a sample that has run out of rows re-reads
+                            // its last one (as an empty range).  The rows behind it may never have been loaded, and
+                            // an arbitrary prefix value would send the unconditional slot loads outside the ring
+                            if (r + 1u < nrowA) { offA += PS2; if (offA >= Ps + RHPS2) offA = Ps; }
+                            if (r + 1u < nrowB) { offB += PS2; if (offB >= Ps + RHPS2) offB = Ps; }
                         }
                         }
                         cnt += ((dminA <= r2) ? 1u : 0u) + ((dminB <= r2) ? 1u : 0u);

@@ -522,3 +522,24 @@ def test_full_size_config5_both_algorithms(ctx):
     auto = ctx.render_grainwise(fg_params_from(pg, dg, path=0), lamg, offg)
     assert np.array_equal(tile, glob) and np.array_equal(auto, glob)
     assert abs(float(glob.mean()) - float(img.mean()) / 255.0) < 0.03  # E[pixel] ~ u (Boolean-model identity; exact for constant input)
+
+
+def test_mixed_row_counts_never_read_rows_outside_the_window(ctx):
+    """r = 0.12 (delta = 1/9, rm = 0.12): samples visit 3 or 4 cell rows, so a pair can mix row counts and the
+    shorter sample idles while the longer one finishes.  It used to step on to the next ring row -- possibly
+    one the window never loaded, whose arbitrary prefix value sent the unconditional slot loads outside the
+    grain ring (an illegal shared-memory read on 1024^2 'natural', N = 128, seed 5490, found by the
+    benchmarks/ sweep).  Same configuration: runs, and staged == tiled == direct on a band."""
+    from tools.bench_sweep_b200 import intensity_field
+    img = intensity_field("natural", 1024)
+    for seed in (5489, 5490, 5491):
+        p = O.make_params(radius=0.12, n_samples=128, algo=O.ALGO_PIXEL, seed=seed)
+        d, off, off_in = O.derive_common(p, 1024, 1024)
+        lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
+        full = ctx.render_pixelwise(fg_params_from(p, d, path=3), lam, off_in)
+        a, b = 300, 316
+        band = {}
+        for path in (1, 2):
+            band[path] = np.zeros_like(full)
+            ctx.render_pixelwise(fg_params_from(p, d, path=path, rows=(a, b)), lam, off_in, out=band[path])
+        assert np.array_equal(full[a:b], band[1][a:b]) and np.array_equal(band[2][a:b], band[1][a:b])
