@@ -132,10 +132,11 @@ def oracle_sample(wl: dict, img: np.ndarray, seconds: float, nthreads: int = 0):
         rows = int(max(threads, min(oh - y0, threads * seconds / dt)))
         c = O.Counters()
         t = time.perf_counter()
-        O.render_pixelwise(lam, p, d, off_in, y0, y0 + rows, nthreads, c)
+        ref = O.render_pixelwise(lam, p, d, off_in, y0, y0 + rows, nthreads, c)
         dt = time.perf_counter() - t
         evals = c.sample_evals
         return dict(rate=evals / dt, seconds=dt, threads=threads, rows=rows, evals=evals,
+                    ref_rows=(y0, y0 + rows, ref[y0:y0 + rows].copy()),  # plane 0, for the bitwise check against the GPU image
                     n_cell=c.cell_visits / max(1, evals), n_test=c.grain_tests / max(1, evals),
                     sample=f"{rows} output rows x {d.output_width} px x {wl['n']} samples of plane 0, {threads} threads")
     # grain-wise: a centred square crop sized for the budget
@@ -148,13 +149,14 @@ def oracle_sample(wl: dict, img: np.ndarray, seconds: float, nthreads: int = 0):
         lam = O.lambda_plane(O.normalize_plane(plane), d.inv_e_pi_r2)
         c = O.Counters()
         t = time.perf_counter()
-        O.render_grainwise(lam, p, d, off, nthreads, c)
+        ref = O.render_grainwise(lam, p, d, off, nthreads, c)
         dt = time.perf_counter() - t
         if dt > seconds / 4 or side * 2 > min(wl["w"], wl["h"]):
             break
         side *= 2
     evals = d.output_width * d.output_height * wl["n"]
     return dict(rate=evals / dt, seconds=dt, threads=threads, rows=side, evals=evals, n_cell=0.0, n_test=0.0,
+                ref_crop=(side, ref),  # the crop's own render: equals the full render away from the crop's right/bottom edge
                 sample=f"{side}x{side} crop x {wl['n']} samples, {threads} threads")
 
 
@@ -213,6 +215,96 @@ def run_reference(args, wl, rank, world):
     print(json.dumps(line, default=float), flush=True)
 
 
+class Prepared:
+    """Host-side derivation of one workload, exactly as the reference host does it (ParamsBuilder -> Derived)."""
+
+    def __init__(self, name: str):
+        import film_grain_b200 as fg
+        from film_grain_b200 import host as H
+        self.name = name
+        wl = self.wl = WORKLOADS[name]
+        self.img = synth_image(wl["image"], wl["w"], wl["h"])
+        self.params = H.ParamsBuilder(radius_mean=wl["radius"], n_samples=wl["n"], zoom=wl["zoom"],
+                                      algo=H.Algo.Pixel if wl["algo"] == "pixel" else H.Algo.Grain,
+                                      color_mode=H.ColorMode.Rgb if wl["planes"] == 3 else H.ColorMode.Luma).build()
+        d = self.d = H.derive_common(self.params, (wl["w"], wl["h"]))
+        self.planes = wl["planes"]
+        self.lam_host = [H.lambda_plane((self.img[:, :, c].astype(np.float32) / np.float32(255.0)).astype(np.float32), d.inv_e_pi_r2)
+                         for c in range(self.planes)]
+        self.offsets = d.offsets_input if wl["algo"] == "pixel" else d.offsets
+        self.algo = fg.FG_ALGO_PIXEL if wl["algo"] == "pixel" else fg.FG_ALGO_GRAIN
+        self.out_w, self.out_h = d.output_width, d.output_height
+
+    def block(self, rows=None):
+        from film_grain_b200 import host as H
+        return H._band(self.d.block, rows)
+
+    def mpx_samples(self, ms: float) -> float:
+        return self.out_w * self.out_h * self.wl["n"] / (ms * 1e-3) / 1e6
+
+
+def check_against_oracle(prep: Prepared, sm: dict, image0) -> dict:
+    """Bitwise comparison of plane 0 of a finished GPU image (numpy [out_h, out_w]) with what the CPU oracle
+    rendered for the cpu_baseline leg (rows of the same workload / a top-left crop for grain-wise)."""
+    if "ref_rows" in sm:
+        a, b, ref = sm["ref_rows"]
+        ok = bool(np.array_equal(ref, image0[a:b]))
+        return {"against": "oracle", "rows": [int(a), int(b)], "plane": 0, "pixels": int(ref.size),
+                "result": "bitwise-equal" if ok else "MISMATCH"}
+    side, ref = sm["ref_crop"]
+    m = side - 16  # grains outside the crop reach its last rows / columns only
+    ok = bool(np.array_equal(ref[:m, :m], image0[:m, :m]))
+    return {"against": "oracle", "crop": [0, 0, int(m), int(m)], "plane": 0, "pixels": int(m * m),
+            "result": "bitwise-equal" if ok else "MISMATCH"}
+
+
+def quick_workload(ctx, name: str, dev, stream, flush, cpu_seconds: float, steps: int = 3, warmup: int = 3) -> dict:
+    """The other BASELINE configs, driver-visible: device-resident value with its own clock record, a short CPU
+    baseline and a bitwise check of the GPU image against the oracle's sample (rank 0, one GPU)."""
+    import torch
+    prep = Prepared(name)
+    blk = prep.block()
+    d_lam = torch.from_numpy(np.stack(prep.lam_host)).to(dev)
+    d_off = torch.from_numpy(np.ascontiguousarray(prep.offsets)).to(dev)
+    d_out = torch.zeros((prep.planes, prep.out_h, prep.out_w), dtype=torch.float32, device=dev)
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            ctx.render_planes_device(blk, prep.algo, prep.planes, d_lam.data_ptr(), d_off.data_ptr(), d_out.data_ptr(), sync=False)
+        stream.synchronize()
+        sampler = ClockSampler(dev.index or 0)
+        sampler.start()
+        total, strip, table = 0.0, 0.0, 0.0
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            ctx.render_planes_device(blk, prep.algo, prep.planes, d_lam.data_ptr(), d_off.data_ptr(), d_out.data_ptr(), sync=False)
+            b.record(stream)
+            stream.synchronize()
+            total += a.elapsed_time(b)
+            st = ctx.stats()
+            strip += float(st.strip_ms)
+            table += float(st.table_ms)
+        # short renders: keep the sampler alive for a few of its periods so that it sees the GPU under load
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            ctx.render_planes_device(blk, prep.algo, prep.planes, d_lam.data_ptr(), d_off.data_ptr(), d_out.data_ptr(), sync=False)
+            stream.synchronize()
+        clocks = sampler.stop()
+    st = ctx.stats()
+    ms = total / steps
+    res = {"workload": prep.wl["desc"], "value": prep.mpx_samples(ms), "unit": "Mpixel*samples/s", "ms_per_step": ms,
+           "steps": steps, "warmup": warmup, "clocks": clocks, "gpu_launches_per_step": int(st.launches),
+           "tiles": int(st.tiles_total), "tiles_fallback": int(st.tiles_fallback),
+           "kernel_ms": {"evaluate_or_rasterise": strip / steps, "generate": table / steps}}
+    sm = oracle_sample(prep.wl, prep.img, cpu_seconds, host_threads())
+    res["cpu_baseline"] = {"value": sm["rate"] / prep.planes / 1e6, "unit": "Mpixel*samples/s", "cores": sm["threads"],
+                           "kind": "port", "sample": sm["sample"], "seconds": sm["seconds"]}
+    res["image_check"] = check_against_oracle(prep, sm, d_out[0].cpu().numpy())
+    del d_lam, d_off, d_out
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -223,6 +315,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=None,
                     help="budget of the CPU sample (default: 12 s for cpu_baseline; ~90 s over all steps of --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_workloads block (C1/C3/C4/C5 beside the headline)")
     ap.add_argument("--bands", default="auto", choices=["auto", "peer", "gather"],
                     help="N > 1: how the finished bands reach GPU 0 (peer = the kernels store straight into GPU 0's image "
                          "over NVLink; gather = NCCL gather; auto = peer when it can be set up)")
@@ -241,7 +334,6 @@ def main():
     import torch.distributed as dist
 
     import film_grain_b200 as fg
-    from film_grain_b200 import host as H
     from film_grain_b200.dist import PeerImage, band_rows, gather_bands
 
     if not torch.cuda.is_available():
@@ -258,20 +350,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
 
-    # ---- host-side derivation exactly as the reference host does it (ParamsBuilder -> Derived) ----
-    img = synth_image(wl["image"], wl["w"], wl["h"])
-    params = H.ParamsBuilder(radius_mean=wl["radius"], n_samples=wl["n"], zoom=wl["zoom"],
-                             algo=H.Algo.Pixel if wl["algo"] == "pixel" else H.Algo.Grain,
-                             color_mode=H.ColorMode.Rgb if wl["planes"] == 3 else H.ColorMode.Luma).build()
-    d = H.derive_common(params, (wl["w"], wl["h"]))
-    planes = wl["planes"]
-    lam_host = [H.lambda_plane((img[:, :, c].astype(np.float32) / np.float32(255.0)).astype(np.float32), d.inv_e_pi_r2)
-                for c in range(planes)]
-    offsets = d.offsets_input if wl["algo"] == "pixel" else d.offsets
-    algo = fg.FG_ALGO_PIXEL if wl["algo"] == "pixel" else fg.FG_ALGO_GRAIN
-    out_w, out_h = d.output_width, d.output_height
+    prep = Prepared(args.workload)
+    img, d, planes, lam_host, offsets, algo = prep.img, prep.d, prep.planes, prep.lam_host, prep.offsets, prep.algo
+    out_w, out_h = prep.out_w, prep.out_h
     rb, re = band_rows(out_h, rank, world)
-    blk = H._band(d.block, (rb, re) if world > 1 else None)
+    blk = prep.block((rb, re) if world > 1 else None)
 
     ctx = fg.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -288,6 +371,7 @@ def main():
     torch.cuda.synchronize()
 
     def step_device():
+        """One step; returns the finished image on rank 0 as [planes, out_h, out_w] (None elsewhere)."""
         if peer is not None:
             # every rank's kernels write their band rows straight into GPU 0's image; one device-side
             # barrier on the engine's stream ends the step
@@ -298,7 +382,7 @@ def main():
         if world > 1:  # finished image resident on GPU 0: gather the row bands (NCCL over NVLink)
             band = d_out[:, rb:re, :].permute(1, 0, 2).contiguous()
             full = gather_bands(band, out_h, rank, world)
-            return full
+            return full.permute(1, 0, 2) if full is not None else None
         return d_out
 
     launches = 0
@@ -338,7 +422,26 @@ def main():
     total_ms, strip_total_ms, table_total_ms = float(tt[0]), float(tt[1]), float(tt[2])
     strip_launches = max(1, int(ctx.stats().strip_launches)) if algo == fg.FG_ALGO_PIXEL else 1
     ms_per_step = total_ms / args.steps
-    value = out_w * out_h * wl["n"] / (ms_per_step * 1e-3) / 1e6
+    value = prep.mpx_samples(ms_per_step)
+
+    # ---- image check, outside the timed region: the image the timed steps produce, bit for bit ----
+    # N > 1: the image assembled from the ranks' bands against a single-GPU render of the whole image, computed by
+    # rank 0 in this process.  N = 1: against the CPU oracle's rows (below, with cpu_baseline) and the host-buffer call.
+    image_check = None
+    with torch.cuda.stream(stream):
+        assembled = step_device()
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+            if rank == 0:
+                single = torch.empty((planes, out_h, out_w), dtype=torch.float32, device=dev)
+                ctx.render_planes_device(prep.block(None), algo, planes, d_lam.data_ptr(), d_off.data_ptr(), single.data_ptr(), sync=True)
+                same = bool(torch.equal(assembled, single))
+                image_check = {"against": "single-GPU render of the whole image in the same process (rank 0)",
+                               "pixels": int(single.numel()), "result": "bitwise-equal" if same else "MISMATCH"}
+                del single
+            dist.barrier()
+        device_image0 = assembled[0].cpu().numpy() if rank == 0 else None
 
     # ---- e2e: the reference-facing C-ABI call with HOST buffers (copies inside the timed region) ----
     e2e = None
@@ -355,26 +458,50 @@ def main():
             ctx.render_planes(blk, algo, lam_pinned, offsets, host_outs)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         s = ctx.stats()
-        e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
+        e2e = {"value": prep.mpx_samples(e2e_ms), "unit": "Mpixel*samples/s",
                "h2d_bytes_per_step": int(s.h2d_bytes), "d2h_bytes_per_step": int(s.d2h_bytes),
                "ms_per_step": e2e_ms, "h2d_ms": float(s.h2d_ms), "kernel_ms": float(s.kernel_ms), "d2h_ms": float(s.d2h_ms),
+               "equals_device_image": bool(np.array_equal(host_outs[0], device_image0)),
                "call": "fg_render_planes (pinned host f32 lambda planes in, f32 planes out; the output planes are one page-locked "
                        "block, which the kernels write in place over PCIe -- d2h_ms is the staged copy, 0 when in place)"}
+        # The seam's own call pattern (src/color.rs:56-60, src/lib.rs:154-158): one fg_render_pixelwise / _grainwise per
+        # colour plane, sequentially, on PAGEABLE buffers (a Rust Vec<f32>): staged copies both ways, per-plane set-up.
+        seam_out = [np.empty((out_h, out_w), np.float32) for _ in range(planes)]
+        seam_lam = [np.array(l, copy=True) for l in lam_host]
+        one = ctx.render_pixelwise if algo == fg.FG_ALGO_PIXEL else ctx.render_grainwise
+
+        def step_seam():
+            for c in range(planes):
+                one(blk, seam_lam[c], offsets, out=seam_out[c])
+        step_seam()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_seam()
+        seam_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e["seam"] = {"value": prep.mpx_samples(seam_ms), "unit": "Mpixel*samples/s", "ms_per_step": seam_ms,
+                       "h2d_bytes_per_step": int(sum(l.nbytes for l in seam_lam) + planes * offsets.nbytes),
+                       "d2h_bytes_per_step": int(sum(o.nbytes for o in seam_out)),
+                       "equals_device_image": bool(np.array_equal(seam_out[0], device_image0)),
+                       "call": f"{planes} x fg_render_{'pixelwise' if algo == fg.FG_ALGO_PIXEL else 'grainwise'} in sequence on pageable "
+                               "numpy buffers (what render_from_workspace_impl does per plane, src/lib.rs:146-166)"}
+        del seam_out, seam_lam
         # the fused u8 entry point: 8-bit RGB over PCIe instead of f32 planes
         if planes == 3 and wl["algo"] == "pixel":
             pin_img = torch.from_numpy(np.ascontiguousarray(img)).pin_memory()
             pin_out8 = torch.empty((out_h, out_w, 3), dtype=torch.uint8).pin_memory()
-            img, out8 = pin_img.numpy(), pin_out8.numpy()
+            img8, out8 = pin_img.numpy(), pin_out8.numpy()
             for _ in range(2):
-                ctx.render_rgb8(blk, algo, fg.FG_COLOR_RGB, img, offsets, out8)
+                ctx.render_rgb8(blk, algo, fg.FG_COLOR_RGB, img8, offsets, out8)
             t0 = time.perf_counter()
             for _ in range(args.steps):
-                ctx.render_rgb8(blk, algo, fg.FG_COLOR_RGB, img, offsets, out8)
+                ctx.render_rgb8(blk, algo, fg.FG_COLOR_RGB, img8, offsets, out8)
             f_ms = (time.perf_counter() - t0) * 1e3 / args.steps
             s8 = ctx.stats()
-            e2e["fused_rgb8"] = {"value": out_w * out_h * wl["n"] / (f_ms * 1e-3) / 1e6, "ms_per_step": f_ms,
+            e2e["fused_rgb8"] = {"value": prep.mpx_samples(f_ms), "ms_per_step": f_ms,
                                  "h2d_bytes_per_step": int(s8.h2d_bytes), "d2h_bytes_per_step": int(s8.d2h_bytes),
                                  "call": "fg_render_rgb8 (host u8 RGB in/out, colour fused on device)"}
+            del pin_img, pin_out8, img8, out8
+        del pin_lam, pin_res, lam_pinned, host_outs
     else:
         from film_grain_b200.dist import SharedHostImage
         shared = SharedHostImage.create((planes, out_h, out_w), rank, world, dev) if args.bands != "gather" else None
@@ -402,10 +529,12 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             dist.all_reduce(tb, op=dist.ReduceOp.SUM)
             e2e_ms = float(tmax[0])
-            e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
+            e2e = {"value": prep.mpx_samples(e2e_ms), "unit": "Mpixel*samples/s",
                    "h2d_bytes_per_step": int(tb[1]), "d2h_bytes_per_step": int(tb[2]), "ms_per_step": e2e_ms,
+                   "equals_device_image": bool(np.array_equal(shared.array[0], device_image0)) if rank == 0 else None,
                    "call": "per rank: fg_render_planes on its row band (pinned host lambda in, band-restricted upload; output = one "
                            "page-locked host image shared by all ranks, written in place by the kernels) + barrier; bytes summed over ranks"}
+            del host_outs, lam_pinned, pin_lam
             shared.close()
         else:
             # each rank uploads only the lambda rows its band can see: band / zoom +- (max |offset| + rm) plus slack
@@ -413,8 +542,7 @@ def main():
             in_r0 = max(0, int(np.floor(rb / wl["zoom"] - reach)))
             in_r1 = min(wl["h"], int(np.ceil(re / wl["zoom"] + reach)) + 1)
             pin_in = torch.from_numpy(np.stack(lam_host)[:, in_r0:in_r1, :].copy()).pin_memory()
-            pin_shape = (planes, out_h, out_w) if peer is not None else (out_h, planes, out_w)
-            pin_out = torch.empty(pin_shape, dtype=torch.float32).pin_memory() if rank == 0 else None
+            pin_out = torch.empty((planes, out_h, out_w), dtype=torch.float32).pin_memory() if rank == 0 else None
             with torch.cuda.stream(stream):
                 def step_e2e():
                     if peer is not None:
@@ -435,11 +563,12 @@ def main():
             t2 = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
             e2e_ms = float(t2[0])
-            e2e = {"value": out_w * out_h * wl["n"] / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel*samples/s",
+            e2e = {"value": prep.mpx_samples(e2e_ms), "unit": "Mpixel*samples/s",
                    "h2d_bytes_per_step": int(pin_in.numel() * 4), "d2h_bytes_per_step": int(planes * out_w * out_h * 4),
                    "ms_per_step": e2e_ms,
                    "call": "per rank: pinned H2D of the lambda rows its band sees + band render + "
                            + ("peer stores into GPU 0's image + barrier" if peer is not None else "NCCL band gather") + "; rank 0: D2H of the image"}
+            del pin_in, pin_out
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -451,29 +580,36 @@ def main():
             sm = oracle_sample(wl, img, args.cpu_seconds or 12.0, host_threads())
             n_cell, n_test = (sm["n_cell"], sm["n_test"]) if wl["algo"] == "pixel" else (n_cell, n_test)
             cpu = {"value": sm["rate"] / planes / 1e6, "unit": "Mpixel*samples/s", "cores": sm["threads"], "kind": "port",
-                   "sample": sm["sample"], "seconds": sm["seconds"]}
+                   "sample": sm["sample"], "seconds": sm["seconds"],
+                   "note": "the port skips Poisson::new's ln / sqrt / log_gamma for lambda' < 12 (only exp(-lambda') is used on that "
+                           "branch), i.e. it does a little LESS work per cell visit than the Rust: the GPU/CPU ratio is conservative"}
+            image_check = check_against_oracle(prep, sm, device_image0)
         if wl["algo"] == "pixel":
             ao = algorithmic_ops(wl, d.block, d.offsets_input, n_cell, n_test)
-            # dominant kernel: k_pixelwise_strip (evaluation).  Its algorithmic work is the evaluation
-            # term of SURVEY 8(d); the generation term belongs to the bitmap + cell-table kernels that
+            # dominant kernel: the evaluation kernel (k_pixelwise_skew / k_pixelwise_strip).  Its algorithmic work is the
+            # evaluation term of SURVEY 8(d); the generation term belongs to the bitmap + cell-table kernels that
             # run before it and is reported beside it ("table") and in the whole-step figure ("pipeline").
             kernel_ms = (strip_total_ms / args.steps) if strip_total_ms > 0 else ms_per_step
             tab_ms = table_total_ms / args.steps
             achieved = ao["ops_eval"] / strip_launches / (kernel_ms * 1e-3) / 1e12
-            traffic, issue_active = None, None
+            traffic, issue_active, prof_src = None, None, None
             prof = os.path.join(ROOT, "profiles", "strip_dram_bytes.json")
             if os.path.exists(prof):
                 try:
                     pj = json.load(open(prof))
                     traffic, issue_active = pj.get(args.workload), pj.get(args.workload + "_issue_active")
+                    prof_src = pj.get("source")
                 except Exception:
                     traffic = None
             io_bytes = planes * (wl["w"] * wl["h"] * 16 + out_w * out_h * 4)  # thr+e planes in, f32 plane out
             peak = issue["ffma"] / 1e3 * world  # aggregate over the GPUs that shared the launch's work
             roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s",
                     "frac": achieved / peak, "traffic": traffic,
-                    "issue_slots_filled": issue_active,  # ncu smsp__issue_active of the committed capture (executed, not algorithmic, instructions)
-                    "kernel": "k_pixelwise_strip", "kernel_ms": kernel_ms, "share_of_step": kernel_ms / ms_per_step,
+                    "issue_slots_filled": issue_active,
+                    "static": {"traffic": True, "issue_slots_filled": True, "source": prof_src,
+                               "note": "traffic (dram__bytes_read + write) and issue_slots_filled (smsp__issue_active) are NOT measured in this "
+                                       "run: they are read from the committed ncu capture of the same kernel and workload"},
+                    "kernel": ctx.eval_kernel_name(), "kernel_ms": kernel_ms, "share_of_step": kernel_ms / ms_per_step,
                     "launches_per_step": strip_launches,
                     "table": {"kernels": "k_thresholds + k_first_draw_bitmap + k_row_expect + k_row_bases + k_gen_rows",
                               "ms": tab_ms, "share_of_step": tab_ms / ms_per_step,
@@ -505,7 +641,8 @@ def main():
             peak = issue["ffma"] / 1e3 * world
             achieved = ops_r / (kernel_ms * 1e-3) / 1e12
             roof = {"bound": "alu", "achieved": achieved, "peak": peak, "unit": "Tlane-op/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "k_gw_tile (last plane)", "kernel_ms": kernel_ms, "share_of_step": kernel_ms * planes / ms_per_step,
+                    "traffic": None, "kernel": ctx.eval_kernel_name() + " (last plane)", "kernel_ms": kernel_ms,
+                    "share_of_step": kernel_ms * planes / ms_per_step,
                     "launches_per_step": planes,
                     "generation": {"kernels": "k_gw_count + scan + k_gw_fill", "ms": tab_ms,
                                    "achieved": (ops_g / planes / (tab_ms * 1e-3) / 1e12) if tab_ms > 0 else None},
@@ -515,6 +652,15 @@ def main():
                                   "box_pixels": (2.0 * r_out) ** 2, "ops_raster": ops_r, "ops_gen": ops_g},
                     "peak_source": "FFMA issue rate measured in this run (fg_measure_issue_peak)",
                     "issue_peaks_glaneops": issue}
+        others = None
+        if world == 1 and args.workload == "c2" and not args.no_others and not args.no_cpu:
+            # the other BASELINE configs beside the headline, each with its own clocks, CPU sample and oracle check
+            others = {}
+            for name in ("c1", "c3", "c4", "c5"):
+                try:
+                    others[name] = quick_workload(ctx, name, dev, stream, flush, cpu_seconds=3.0)
+                except Exception as e:  # never lose the headline line to a side measurement
+                    others[name] = {"error": repr(e)[:300]}
         line = {
             "metric": "Mpixel*samples/s", "value": value, "unit": "Mpixel*samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -525,22 +671,35 @@ def main():
                                                           if peer is not None else "NCCL gather to GPU 0")),
                        "l2": "flushed between timed iterations (256 MiB memset outside the events)",
                        "tiles": tiles_total, "tiles_fallback": tiles_fb},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "image_check": image_check,
+            "roofline": roof, "cpu_baseline": cpu, "other_workloads": others,
         }
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line, default=float), flush=True)
-    # teardown: torch's device and pinned-host allocators record events on every stream a block was
-    # used on -- including the engine's stream -- when blocks are released at interpreter exit, i.e.
-    # after the context may already have destroyed that stream.  Synchronise, tear the process group
-    # down, and leave without running destructors.
+    # Teardown in dependency order, then a NORMAL interpreter exit (atexit hooks and finalizers run).  torch's caching
+    # allocators record an event on every stream a block was used on when the block is released -- including the
+    # engine's stream -- so every tensor goes first and the caches are emptied while that stream is still alive; the
+    # engine context (which owns the stream) is closed last.
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    del d_lam, d_off, d_out, flush
+    peer = None
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    try:
+        torch._C._host_emptyCache()  # pinned-host cache (torch >= 2.5); absent: the blocks are event-free by now
+    except Exception:
+        pass
+    if world > 1:
         dist.destroy_process_group()
+    del stream
+    # the context is deliberately NOT destroyed: process exit releases it, and any block torch still holds can
+    # record its event on a live stream
+    ctx.leak()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 if __name__ == "__main__":

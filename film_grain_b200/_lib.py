@@ -67,11 +67,13 @@ ABI = {
     "fg_context_create": (C.c_int, [_P(_VP), C.c_int]),
     "fg_context_destroy": (None, [_VP]),
     "fg_last_error": (C.c_char_p, [_VP]),
+    "fg_last_eval_kernel": (C.c_char_p, [_VP]),
     "fg_set_cancel_flag": (None, [_VP, _P(C.c_int)]),
     "fg_get_stats": (None, [_VP, _P(FgStats)]),
     "fg_render_pixelwise": (C.c_int, [_VP, _P(FgParams), _VP, _VP, _VP]),
     "fg_render_grainwise": (C.c_int, [_VP, _P(FgParams), _VP, _VP, _VP]),
     "fg_render_planes": (C.c_int, [_VP, _P(FgParams), C.c_int, C.c_int, _P(_VP), _VP, _P(_VP)]),
+    "fg_render_planes_cancelable": (C.c_int, [_VP, _P(FgParams), C.c_int, C.c_int, _P(_VP), _VP, _P(_VP), _P(C.c_int)]),
     "fg_render_planes_device": (C.c_int, [_VP, _P(FgParams), C.c_int, C.c_int, _VP, _VP, _VP, C.c_int]),
     "fg_context_stream": (C.c_uint64, [_VP]),
     "fg_context_synchronize": (C.c_int, [_VP]),

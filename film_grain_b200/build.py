@@ -10,9 +10,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfg_b200.so")
 SOURCES = ["fg_api.cu", os.path.join("..", "host", "film_grain.cpp")]
-DEPS = ["fg_api.cu", "fg_ctx.cuh", "fg_kernels.cuh", "fg_rng.cuh", "fg_tile.cuh", "fg_stage.cuh", "fg_color.cuh",
-        "fg_zig_tables.h", "fg_logf.h", os.path.join("..", "..", "include", "fg.h"), os.path.join("..", "..", "include", "fg_host.h"),
-        os.path.join("..", "host", "film_grain.cpp"), os.path.join("..", "host", "film_grain.hpp")]
+
+
+def deps() -> list[str]:
+    """Every file the library is compiled from: globbed, so a new header cannot be forgotten."""
+    import glob
+    out = []
+    for pat in ("csrc/*.cu", "csrc/*.cuh", "csrc/*.h", "host/*", "../include/*.h"):
+        out += glob.glob(os.path.join(HERE, pat))
+    return out
 
 
 def nvcc_path() -> str:
@@ -26,7 +32,7 @@ def is_stale() -> bool:
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:

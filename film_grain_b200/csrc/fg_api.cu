@@ -136,10 +136,20 @@ int pixelwise_device(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         int rc = tile_render(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, path);
         if (rc != 1) return rc; // 1 = "tiled path not applicable, use direct"
     }
-    dim3 grid((p->out_w + 31) / 32, (band_rows + 7) / 8, n_planes), block(32, 8);
-    k_pixelwise_direct<<<grid, block, 0, ctx->stream>>>(d_lambda, in_stride, (const float2*)d_offsets, d_out, out_stride, c);
-    ctx->stats.launches += 1;
-    FG_CUDA(ctx, cudaGetLastError());
+    // grid.y is limited to 65 535 CTAs of 8 rows: taller bands (validate() admits 2^30 rows) go in row chunks
+    const int rows_per_launch = 65535 * 8;
+    for (int y = c.row_begin; y < c.row_end; y += rows_per_launch) {
+        RenderConsts cb = c;
+        cb.row_begin = y;
+        cb.row_end = std::min(c.row_end, y + rows_per_launch);
+        dim3 grid((p->out_w + 31) / 32, (unsigned)((cb.row_end - cb.row_begin + 7) / 8), n_planes), block(32, 8);
+        k_pixelwise_direct<<<grid, block, 0, ctx->stream>>>(d_lambda, in_stride, (const float2*)d_offsets, d_out, out_stride, cb);
+        ctx->eval_kernel = "k_pixelwise_direct";
+        ctx->stats.launches += 1;
+        FG_CUDA(ctx, cudaGetLastError());
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    }
+    (void)band_rows;
     return FG_OK;
 }
 
@@ -243,6 +253,7 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     if (tiled) {
         const int tiles_x = (int)((p->out_w + FG_GT_W - 1) / FG_GT_W), tiles_y = (c.row_end - c.row_begin + FG_GT_H - 1) / FG_GT_H;
         if (tiles_x > 0 && tiles_y > 0) {
+            ctx->eval_kernel = "k_gw_tile";
             k_gw_tile<<<(unsigned)tiles_x * (unsigned)tiles_y, FG_GT_THREADS, sizeof(GwTileSmem), ctx->stream>>>(
                 (const GrainRec*)ctx->grains.p, (const uint64_t*)ctx->scan_out.p, npix_in, d_total, iy0, iy1, (const float2*)d_offsets,
                 d_out, tiles_x, c);
@@ -256,6 +267,7 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
         if ((rc = ensure(ctx, ctx->bits, band_pix * lanes32 * sizeof(uint32_t)))) return rc;
         FG_CUDA(ctx, cudaMemsetAsync(ctx->bits.p, 0, band_pix * lanes32 * sizeof(uint32_t), ctx->stream));
     }
+    ctx->eval_kernel = "k_gw_splat + k_gw_reduce";
     k_gw_reduce<<<(unsigned)((band_pix + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t*)ctx->bits.p, lanes32, d_out, c);
     FG_CUDA(ctx, cudaGetLastError());
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -321,9 +333,10 @@ float* mapped_host_planes(float* const* out, int n_planes, size_t out_elems) {
 }
 
 int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
-                       const float* offsets, float* const* out) {
+                       const float* offsets, float* const* out, const volatile int* cancel = nullptr) {
     if (!ctx) return FG_ERR_INVALID;
     std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedCallCancel call_cancel(ctx, cancel);
     ScopedDevice dev(ctx->device);
     ctx->err.clear();
     ctx->stats = fg_stats{};
@@ -456,6 +469,7 @@ void fg_context_destroy(fg_ctx* ctx) {
 }
 
 const char* fg_last_error(const fg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+const char* fg_last_eval_kernel(const fg_ctx* ctx) { return ctx ? ctx->eval_kernel : ""; }
 void fg_set_cancel_flag(fg_ctx* ctx, const volatile int* flag) { if (ctx) ctx->cancel = flag; }
 void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
     if (!ctx || !out) return;
@@ -494,6 +508,11 @@ int fg_render_grainwise(fg_ctx* ctx, const fg_params* p, const float* lambda, co
 int fg_render_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
                      const float* offsets, float* const* out) {
     return render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out);
+}
+
+int fg_render_planes_cancelable(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
+                                const float* offsets, float* const* out, const volatile int* cancel) {
+    return render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out, cancel);
 }
 
 int fg_render_planes_device(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* d_lambda,

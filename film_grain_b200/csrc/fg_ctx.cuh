@@ -29,7 +29,8 @@ struct fg_ctx {
     cudaEvent_t ev[7] = {};
     std::mutex mu;
     std::string err;
-    const volatile int* cancel = nullptr;
+    const volatile int* cancel = nullptr;      // fg_set_cancel_flag: stays until replaced
+    const volatile int* call_cancel = nullptr; // the flag of the running *_cancelable call (set and cleared under mu)
     fg_stats stats{};
     int sm_count = 0;
     size_t smem_optin = 0;
@@ -40,6 +41,7 @@ struct fg_ctx {
     bool fb_pending = false;
     size_t table_max = (size_t)48 << 30; // cell-table budget per band (FG_B200_TABLE_MAX_BYTES overrides; tests)
     double table_slack_sigma = 8.0; // row capacity = expected grains + this many sigma + 64 (FG_B200_TABLE_SLACK_SIGMA: tests)
+    const char* eval_kernel = ""; // name of the kernel that evaluated / rasterised the last render (fg_last_eval_kernel)
     uint32_t strip_launches = 0; // strip-kernel launches of the last pixel-wise render (row sub-bands)
 };
 
@@ -103,6 +105,16 @@ void release(DevBuf& b) {
     b.p = nullptr; b.cap = 0;
 }
 
-bool cancelled(const fg_ctx* ctx) { return ctx->cancel && *ctx->cancel != 0; }
+bool cancelled(const fg_ctx* ctx) {
+    return (ctx->cancel && *ctx->cancel != 0) || (ctx->call_cancel && *ctx->call_cancel != 0);
+}
+bool cancel_armed(const fg_ctx* ctx) { return ctx->cancel || ctx->call_cancel; }
+
+// the per-call cancel flag lives in the context only while the call holds the context mutex
+struct ScopedCallCancel {
+    fg_ctx* ctx;
+    ScopedCallCancel(fg_ctx* c, const volatile int* flag) : ctx(c) { ctx->call_cancel = flag; }
+    ~ScopedCallCancel() { ctx->call_cancel = nullptr; }
+};
 
 } // namespace

@@ -914,7 +914,7 @@ __global__ void __launch_bounds__(256) k_pixelwise_table_tiles(const float* __re
     const uint64_t work = (uint64_t)nt * chunks_per_tile;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const float rm = c.rad.rm, delta = c.delta, r2c = cfg.r2c;
-    const bool radius_ok = LOGN || r2c > 0.0f;
+    const bool radius_ok = LOGN || (c.rad.mean_linear > rm ? rm : c.rad.mean_linear) > 0.0f; // the radius itself: r2c is positive for r < 0
     for (uint64_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
         const TileRef t = tiles[wi / chunks_per_tile];
         const int yl = (int)(wi % chunks_per_tile) * 8 + ty;
@@ -1233,6 +1233,7 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
                      (int)staged, g.TH, g.SEG, g.RH, g.CWB, g.GCAP, g.total, units);
     ctx->stats.tiles_total += units;
     ctx->strip_launches += 1;
+    ctx->eval_kernel = "k_pixelwise_strip";
     return FG_OK;
 }
 

@@ -46,6 +46,15 @@ class Context:
             self._lib.fg_context_destroy(self._h)
             self._h = None
 
+    def leak(self):
+        """Give the native context up without destroying it (it lives until the process exits).  For callers
+        that wrapped the context's stream in another runtime's stream object: that runtime may still record
+        events on the stream while it tears down, after this object is gone."""
+        self._h = None
+
+    def eval_kernel_name(self) -> str:
+        return self._lib.fg_last_eval_kernel(self._h).decode()
+
     def __del__(self):
         try:
             self.close()

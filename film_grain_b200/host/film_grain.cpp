@@ -448,9 +448,7 @@ std::pair<RgbImage, RenderStats> render_with_input_image(const InputImage& input
     if (input.rgb.size() != input.width * input.height * 3) throw RenderError(RenderError::Message, "image buffer size mismatch");
     Derived d = derive_common(params, input.width, input.height);
     Algo algo = choose_algorithm(params, d);
-    auto ctx = cuda::context(device);
-    fg_set_cancel_flag(ctx->raw(), cancel);
-    struct Unset { fg_ctx* c; ~Unset() { fg_set_cancel_flag(c, nullptr); } } unset{ctx->raw()};
+    auto ctx = cuda::context(device); // shared_ptr: the context outlives this call even if another thread invalidates it
     const size_t npix = input.width * input.height, nout = d.output_width * d.output_height;
     const bool luma = params.color_mode == ColorMode::Luma;
     const int n_planes = luma ? 1 : 3;
@@ -480,8 +478,9 @@ std::pair<RgbImage, RenderStats> render_with_input_image(const InputImage& input
     float* op[3];
     for (int c = 0; c < n_planes; ++c) { lp[c] = lambdas[c].data.data(); op[c] = outs[c].data.data(); }
     const bool pixel = algo == Algo::Pixel;
-    int rc = fg_render_planes(ctx->raw(), &q, pixel ? FG_ALGO_PIXEL : FG_ALGO_GRAIN, n_planes, lp,
-                              pixel ? &d.offsets_input[0][0] : &d.offsets[0][0], op);
+    // the cancel flag travels with the call (never stored in the shared context beyond it)
+    int rc = fg_render_planes_cancelable(ctx->raw(), &q, pixel ? FG_ALGO_PIXEL : FG_ALGO_GRAIN, n_planes, lp,
+                                         pixel ? &d.offsets_input[0][0] : &d.offsets[0][0], op, cancel);
     if (rc != FG_OK) cuda::throw_gpu(*ctx, rc, pixel ? "Pixel renderer" : "Grain renderer");
     check_cancel(cancel);
     RgbImage img;
@@ -631,8 +630,19 @@ int fgh_render_with_input_image(const fgh_params* p, const uint8_t* rgb, uint64_
 }
 
 fg_ctx* fgh_context(int device) {
+    // A raw pointer cannot carry the shared_ptr's reference: contexts handed out here are kept alive until the
+    // process ends, so the pointer stays valid across fgh_invalidate_context() and device switches.
+    static std::mutex mu;
+    static std::vector<std::shared_ptr<cuda::GpuContext>> handed_out;
     fg_ctx* out = nullptr;
-    guarded([&] { out = cuda::context(device)->raw(); });
+    guarded([&] {
+        auto sp = cuda::context(device);
+        std::lock_guard<std::mutex> lock(mu);
+        bool known = false;
+        for (auto& h : handed_out) known = known || h.get() == sp.get();
+        if (!known) handed_out.push_back(sp);
+        out = sp->raw();
+    });
     return out;
 }
 

@@ -115,6 +115,10 @@ int fg_context_create(fg_ctx** out, int device);
 void fg_context_destroy(fg_ctx* ctx);
 /* Last error text of this context (valid until the next call on it); "" if none. */
 const char* fg_last_error(const fg_ctx* ctx);
+/* Name of the kernel that evaluated (pixel-wise) / rasterised (grain-wise) the last render of this context:
+ * "k_pixelwise_skew", "k_pixelwise_strip", "k_pixelwise_direct", "k_gw_tile", "k_gw_splat + k_gw_reduce"
+ * (measurement labels; static storage). */
+const char* fg_last_eval_kernel(const fg_ctx* ctx);
 /* Optional cooperative cancel: *flag != 0 is polled between kernel waves. NULL disables. */
 void fg_set_cancel_flag(fg_ctx* ctx, const volatile int* flag);
 /* Statistics of the last render call on this context. */
@@ -140,6 +144,14 @@ int fg_render_grainwise(fg_ctx* ctx, const fg_params* p, const float* lambda,
  * scattered planes take the staged copy.  Same results either way. */
 int fg_render_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes,
                      const float* const* lambda, const float* offsets, float* const* out);
+
+/* Same call with a PER-CALL cancel flag (render_with_input_image_cancelable, src/lib.rs:116-132): *cancel != 0
+ * is polled between the stages and row sub-bands of the render -> FG_ERR_CANCELLED.  The pointer is used only
+ * for the duration of this call (unlike fg_set_cancel_flag, which stays registered), so concurrent callers of
+ * a shared context cannot overwrite or outlive each other's flags.  cancel == NULL: identical to fg_render_planes. */
+int fg_render_planes_cancelable(fg_ctx* ctx, const fg_params* p, int algo, int n_planes,
+                                const float* const* lambda, const float* offsets, float* const* out,
+                                const volatile int* cancel);
 
 /* ---- DEVICE-pointer variants (inputs already resident in HBM; asynchronous on the
  * context stream unless stream_sync != 0).  d_lambda / d_out hold n_planes planes

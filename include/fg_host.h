@@ -64,7 +64,9 @@ int fgh_lambda_from_plane(const float* plane, uint64_t w, uint64_t h, float inv_
 int fgh_render_with_input_image(const fgh_params* p, const uint8_t* rgb, uint64_t w, uint64_t h, int fused,
                                 int device, const volatile int* cancel, uint8_t* rgb_out,
                                 uint64_t out_capacity, fgh_derived* info);
-fg_ctx* fgh_context(int device);       /* process-global cached context; NULL on failure */
+/* process-global cached context; NULL on failure.  The returned pointer stays valid until the process ends
+ * (a context handed out here is not destroyed by fgh_invalidate_context or by a device switch). */
+fg_ctx* fgh_context(int device);
 void fgh_invalidate_context(void);
 /* The libm logf restatement the fused luma path runs on the device (csrc/fg_logf.h), host build:
  * lets the CPU tests compare it with the platform's logf. */

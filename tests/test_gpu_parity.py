@@ -422,6 +422,41 @@ def test_full_size_config3_grainwise_crop_consistency(ctx):
     assert np.array_equal(banded, got)
 
 
+def test_full_size_config3_grainwise_4096_against_the_oracle(ctx):
+    """BASELINE.json configs[2] at FULL size (grain-wise luma 4096x4096 noise, r = 0.5, N = 128; 21 M grains, 2048
+    output tiles): the shared-memory tile rasteriser, the global-mask rasteriser and the engine's own pick, every
+    pixel against the oracle's full render (about 16 s on 8 host threads)."""
+    w = h = 4096
+    p = O.make_params(radius=0.5, n_samples=128, algo=O.ALGO_GRAIN, seed=5489)
+    d, off, off_in = O.derive_common(p, w, h)
+    lam = lambda_from_u8(noise_u8(w, h)[:, :, 0], d.inv_e_pi_r2)
+    ref = O.render_grainwise(lam, p, d, off)
+    for path in (3, 1, 0):
+        got = ctx.render_grainwise(fg_params_from(p, d, path=path), lam, off)
+        bad = np.flatnonzero(ref != got)
+        assert bad.size == 0, f"path {path}: {bad.size} px differ, first at {np.unravel_index(bad[0], ref.shape)}"
+    assert 0.5 < ref.mean() < 0.6
+
+
+def test_full_size_config2_three_plane_render_against_the_oracle(ctx):
+    """BASELINE.json configs[1] exactly as bench.py times it -- ONE batched fg_render_planes call over the three colour
+    planes of the 3840x2160 noise image, r = 0.1, N = 256 -- against the oracle on 48 rows of every plane: 16 at the
+    top edge, 16 in the middle, 16 at the bottom edge (144 rows x 3840 px x 256 samples = 1.4e8 oracle evaluations)."""
+    w, h, n = 3840, 2160, 256
+    p = O.make_params(radius=0.1, n_samples=n, algo=O.ALGO_PIXEL, seed=5489)
+    d, off, off_in = O.derive_common(p, w, h)
+    img = noise_u8(w, h)
+    lams = [lambda_from_u8(img[:, :, c], d.inv_e_pi_r2) for c in range(3)]
+    outs = ctx.render_planes(fg_params_from(p, d), O.ALGO_PIXEL, lams, off_in)
+    st = ctx.stats()
+    assert st.tiles_total > 0
+    for c in range(3):
+        for a, b in ((0, 16), (1072, 1088), (2144, 2160)):
+            ref = O.render_pixelwise(lams[c], p, d, off_in, a, b)
+            bad = np.flatnonzero(ref[a:b] != outs[c][a:b])
+            assert bad.size == 0, f"plane {c} rows {a}..{b}: {bad.size} px differ"
+
+
 def test_multi_gpu_bands_into_peer_image_equal_single_gpu_render():
     """N > 1 (needs >= 2 GPUs, skipped otherwise): every rank renders its row band straight into GPU 0's
     peer-mapped image over NVLink (film_grain_b200/dist.py PeerImage) and, separately, through the NCCL
