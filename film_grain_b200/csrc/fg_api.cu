@@ -11,7 +11,7 @@
 #include <cstdlib>
 #include "fg_ctx.cuh"
 #include "fg_kernels.cuh"
-#include "fg_tile.cuh"
+#include "fg_pixel_host.cuh"
 #include "fg_gw_tile.cuh"
 #include "fg_color.cuh"
 #include "fg_zig_tables.h"

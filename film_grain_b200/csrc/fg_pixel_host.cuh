@@ -1,0 +1,453 @@
+// fg_pixel_host.cuh -- host side of the pixel-wise fast path: geometry plans of the two evaluation kernels
+// (k_pixelwise_skew, fg_skew.cuh; k_pixelwise_strip, fg_tile.cuh), the per-band pipeline
+//   thresholds -> first-draw bitmap -> row capacities -> cell table -> evaluation -> fallback list
+// and the split of a render into row sub-bands (table budget, cancellation points).  Host code only.
+#pragma once
+#include "fg_skew.cuh"
+
+namespace {
+using namespace fg;
+
+struct TilePlan { TileCfg cfg; int spwc; bool ok; };
+
+inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+// Choose the strip geometry for a render; ok == false -> the tiled path does not apply.
+TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, bool staged) {
+    TilePlan pl{};
+    pl.ok = false;
+    if (p->n_samples > (1u << 20)) return pl;
+    const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
+    const double ox = (double)c.off_max_x - (double)c.off_min_x, oy = (double)c.off_max_y - (double)c.off_min_y;
+    const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0;
+    if (!(cwb < 2040.0)) return pl;
+    if (!(2.0 * rm / delta + 3.0 < 250.0)) return pl;   // cell rows per sample are packed in 8 bits
+    const int CWB = (int)cwb;
+    const int PS = staged ? (CWB + 8 + 3) / 4 * 4 : CWB + 2; // staged: + column shift (<= 3) + vector tail (<= 3), multiple of 4
+    const int R = std::max(1, std::min(15, FG_TILE_CELLS / (CWB + 1)));
+    const int spwc = p->n_samples <= 4u * FG_TILE_WARPS ? 4 : (p->n_samples <= 8u * FG_TILE_WARPS ? 8 : FG_TILE_SPW_MAX);
+    const int band = c.row_end - c.row_begin;
+    const size_t smem_max = ctx->smem_optin;
+    const uint32_t bpg = c.rad.lognorm ? 12u : 8u;      // bytes per grain: (cx, cy) [+ r^2]
+    // Largest step height whose window fits; the grain ring takes all remaining shared memory.
+    // pass 0 insists that the ring holds the window at a plausible density (0.45 grains per cell;
+    // iid-uniform 8-bit input averages 1/pi); pass 1 takes anything that fits -- denser content
+    // overflows into the fallback list at run time.
+    for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
+        static const int th_candidates[] = {32, 24, 16, 12, 8, 6, 4, 3, 2, 1};
+        static const int th_forced = std::getenv("FG_B200_TH") ? std::atoi(std::getenv("FG_B200_TH")) : 0; // experiments
+        for (int TH : th_candidates) {
+            if (pl.ok) break;
+            if (th_forced > 0 && TH != th_forced) continue;
+            if (TH > 1 && TH > 2 * band) continue;
+            const double rhb = ((TH - 1) * inv_zoom + oy + 2.0 * rm) / delta + 4.0;
+            if (!(rhb < 30000.0)) continue;
+            const int RH = (int)rhb;
+            TileCfg g{};
+            g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R;
+            uint32_t off = 0;
+            g.off_col = off; off = align_up(off + (staged ? 0u : (uint32_t)CWB * 16u), 16);
+            g.off_P = off; off = align_up(off + (uint32_t)(RH + (staged ? 2 : 0)) * PS * 2u, 16);
+            g.off_list = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
+            g.off_E = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
+            g.off_cnt = off; off = align_up(off + (staged ? 0u : (uint32_t)(FG_TILE_NE + 8) * 4u), 16);
+            g.off_rows = off; off = align_up(off + (staged ? (uint32_t)RH * 28u + 16u : 0u), 16);
+            g.off_wtot = off; off = align_up(off + (uint32_t)(FG_TILE_WARPS + 4) * 4u, 16);
+            g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
+            g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
+            if ((size_t)off + 64 + (size_t)bpg * (2048 + FG_TILE_GPAD) > smem_max) continue;
+            uint32_t gcap = (uint32_t)((smem_max - off - 64) / bpg) - FG_TILE_GPAD;
+            gcap = std::min<uint32_t>(gcap / 64 * 64, 65472u);
+            if (gcap < 2048) continue;
+            if (pass == 0 && (double)gcap < 0.45 * (double)RH * (double)CWB) continue;
+            g.GCAP = (int)gcap;
+            g.off_G = off; off = align_up(off + (gcap + FG_TILE_GPAD) * 8u, 16);
+            g.off_R2 = off;
+            if (c.rad.lognorm) off = align_up(off + (gcap + FG_TILE_GPAD) * 4u, 16);
+            g.total = off;
+            if (off > smem_max) continue;
+            pl.cfg = g;
+            pl.ok = true;
+        }
+    }
+    if (!pl.ok) return pl;
+    TileCfg& g = pl.cfg;
+    g.n_strips = (int)((p->out_w + 31) / 32);
+    // segment height: maximise (wave efficiency over the SMs) x (1 - start-up share).  A segment
+    // regenerates the cell rows of its first window (RH rows = RH*delta*zoom pixel rows of work).
+    const double startup_rows = (double)g.RH * delta * (double)p->zoom * (staged ? 0.05 : 1.0); // staged: a load, not a generation
+    const long long per_seg_units = (long long)g.n_strips * n_planes;
+    int best_n = 1;
+    double best_eff = -1.0;
+    const int max_n = std::max(1, band / std::max(1, 4 * g.TH));
+    auto seg_eff = [&](int n) {
+        int seg = (band + n - 1) / n;
+        seg = (seg + g.TH - 1) / g.TH * g.TH;
+        const int n_eff = (band + seg - 1) / seg;
+        const double waves = (double)per_seg_units * n_eff / ctx->sm_count;
+        return waves / std::ceil(waves) * ((double)seg / ((double)seg + startup_rows));
+    };
+    for (int n = 1; n <= max_n; ++n) best_eff = std::max(best_eff, seg_eff(n));
+    // among near-optimal splits prefer the finest one: more, shorter CTAs balance content-dependent cost
+    for (int n = 1; n <= max_n; ++n)
+        if (seg_eff(n) >= best_eff - 0.01) best_n = n;
+    int seg = (band + best_n - 1) / best_n;
+    seg = (seg + g.TH - 1) / g.TH * g.TH;
+    g.SEG = seg;
+    g.n_segs = (band + seg - 1) / seg;
+    pl.spwc = spwc;
+    return pl;
+}
+
+struct SkewPlan { SkewCfg cfg; int spwc; bool ok; };
+
+// Geometry of k_pixelwise_skew for a render; ok == false -> use k_pixelwise_strip.  `dens` = grains per cell of the
+// band's table (its capacity, i.e. expectation + slack): the merged window of a step must fit shared memory with room
+// for local fluctuations (denser strips go through the fallback list at run time).
+SkewPlan skew_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, double dens) {
+    SkewPlan pl{};
+    pl.ok = false;
+    // Measured on a B200 (profiles/README.md): correct, but at C2 its loader (three copies of every grain, per-step set-up
+    // over only 8 items per warp) costs more than the merged lists save -- 45.7 ms against 36 ms for k_pixelwise_strip.
+    // Kept behind FG_B200_SKEW=1 for experiments and as a third, independent evaluation kernel in the parity tests.
+    static const bool enabled = std::getenv("FG_B200_SKEW") && std::atoi(std::getenv("FG_B200_SKEW")) != 0;
+    if (!enabled || c.rad.lognorm || p->rm != p->delta || p->n_samples > (1u << 20)) return pl;
+    const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
+    const double ox = (double)c.off_max_x - (double)c.off_min_x, oy = (double)c.off_max_y - (double)c.off_min_y;
+    const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0 + 3.0; // + alignment shift
+    if (!(cwb < 2000.0)) return pl;
+    const int CWB = (int)cwb;
+    const int PS = (CWB + 1 + 7) / 8 * 8;
+    const double cpr = inv_zoom / delta; // cell rows per output pixel row
+    if (!(cpr > 0.05 && cpr < 64.0)) return pl;
+    const int spwc = p->n_samples <= 4u * FG_SK_WARPS ? 4 : 8;
+    const int cand = 32 / spwc;
+    const int n_chunks = (int)((p->n_samples + FG_SK_WARPS * spwc - 1) / (FG_SK_WARPS * spwc));
+    const int band = c.row_end - c.row_begin;
+    const double span_rows = oy * (double)p->zoom + 2.0; // pixel rows between the fastest and the slowest sample cursor
+    const size_t smem_max = ctx->smem_optin;
+    static const int th_forced = std::getenv("FG_B200_SKEW_TH") ? std::atoi(std::getenv("FG_B200_SKEW_TH")) : 0; // experiments
+    static const int th_candidates[] = {8, 6, 4, 3, 2, 1};
+    for (int TH : th_candidates) {
+        if (th_forced > 0 && TH != th_forced) continue;
+        if (TH + 1 > cand && TH > 1) continue; // a sample's rows of one step fit one item round
+        const double dr = TH * cpr;
+        int D = std::fabs(dr - std::nearbyint(dr)) < 1e-3 ? (int)std::nearbyint(dr) : (int)std::ceil(dr);
+        D = std::max(1, std::min(D, FG_SK_DMAX));
+        const int S = D + 2;
+        const double rows_per_step = D / cpr;
+        int R = 4;
+        while (R < (int)std::ceil(span_rows + 2.0 * (rows_per_step + 1.0) + 3.0)) R <<= 1;
+        if (R > 2048) continue;
+        SkewCfg g{};
+        g.D = D; g.S = S; g.CWB = CWB; g.PS = PS; g.R = R;
+        uint32_t off = 0;
+        g.off_Ps = off; off = align_up(off + 2u * (uint32_t)S * PS * 2u, 16);
+        g.off_Q = off; off = align_up(off + 2u * (uint32_t)D * PS * 2u, 16);
+        g.off_zero = off; off = align_up(off + (uint32_t)PS * 2u, 16);
+        g.off_info = off; off = align_up(off + 2u * 32u * 16u, 16);
+        g.off_tb = off; off = align_up(off + 2u * 32u * 4u, 16);
+        g.off_wp = off; off = align_up(off + (uint32_t)FG_SK_WARPS * 512u, 16);
+        g.off_pcw = off; off = align_up(off + (uint32_t)FG_SK_WARPS * (uint32_t)(R + 1) * 32u, 16);
+        g.off_sync = off; off = align_up(off + 16u, 16);
+        // segment height (also sizes the chunk accumulator): wave efficiency x (1 - ramp share)
+        g.n_strips = (int)((p->out_w + 31) / 32);
+        const long long per_seg_units = (long long)g.n_strips * n_planes;
+        const double startup_rows = 0.35 * span_rows + rows_per_step;
+        const int seg_cap = n_chunks > 1 ? 64 : 4096;
+        int best_n = 1;
+        double best_eff = -1.0;
+        const int max_n = std::max(1, band / std::max(1, (int)std::ceil(2.0 * rows_per_step)));
+        auto seg_of = [&](int n) { return std::min((band + n - 1) / n, seg_cap); };
+        auto seg_eff = [&](int n) {
+            const int seg = seg_of(n);
+            const int n_eff = (band + seg - 1) / seg;
+            const double waves = (double)per_seg_units * n_eff / ctx->sm_count;
+            return waves / std::ceil(waves) * ((double)seg / ((double)seg + startup_rows));
+        };
+        for (int n = 1; n <= max_n; ++n) best_eff = std::max(best_eff, seg_eff(n));
+        for (int n = 1; n <= max_n; ++n)
+            if (seg_eff(n) >= best_eff - 0.01) best_n = n; // among near-optimal splits the finest: balances content-dependent cost
+        g.SEG = seg_of(best_n);
+        static const int seg_forced = std::getenv("FG_B200_SKEW_SEG") ? std::atoi(std::getenv("FG_B200_SKEW_SEG")) : 0; // experiments
+        if (seg_forced > 0) g.SEG = std::min(seg_forced, seg_cap);
+        g.n_segs = (band + g.SEG - 1) / g.SEG;
+        g.off_pcc = off; off = align_up(off + (n_chunks > 1 ? (uint32_t)g.SEG * 128u : 0u), 16);
+        if ((size_t)off + 2u * 8u * 1024u > smem_max) continue;
+        uint32_t mcap = (uint32_t)((smem_max - off) / 16u); // two buffers of 8-byte grains
+        mcap = std::min<uint32_t>(mcap, 65504u);
+        // every triple owns a fixed range: expectation + room for the fluctuation of a 3-row window (content is
+        // correlated over whole input pixels, so the relative spread does not shrink with the cell size)
+        const uint32_t tcap = mcap / (uint32_t)D / 4u * 4u;
+        const double expect = 3.0 * (double)CWB * dens;
+        if ((double)tcap < 1.8 * expect + 64.0) continue;
+        mcap = tcap * (uint32_t)D;
+        g.MCAP = (int)mcap;
+        g.TCAP = (int)tcap;
+        g.off_M = off; off += 2u * mcap * 8u;
+        g.total = off;
+        if (off > smem_max) continue;
+        pl.cfg = g;
+        pl.spwc = spwc;
+        pl.ok = true;
+        break;
+    }
+    return pl;
+}
+
+template <int SP, bool LG, bool ST>
+cudaError_t strip_attr(int smem) {
+    return cudaFuncSetAttribute(k_pixelwise_strip<SP, LG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+int tile_setup(fg_ctx* ctx) {
+    cudaError_t e;
+    const int smem = (int)ctx->smem_optin;
+#define FG_ATTR(SP)                                                                                               \
+    if ((e = strip_attr<SP, false, false>(smem)) != cudaSuccess || (e = strip_attr<SP, true, false>(smem)) != cudaSuccess || \
+        (e = strip_attr<SP, false, true>(smem)) != cudaSuccess || (e = strip_attr<SP, true, true>(smem)) != cudaSuccess)     \
+        return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_strip)");
+    FG_ATTR(4)
+    FG_ATTR(8)
+    FG_ATTR(FG_TILE_SPW_MAX)
+#undef FG_ATTR
+    if ((e = cudaFuncSetAttribute(k_pixelwise_skew<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_skew<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_skew)");
+    return FG_OK;
+}
+
+template <bool LG, bool ST, typename... Args>
+void launch_strip(int spwc, uint32_t units, uint32_t smem, cudaStream_t s, Args... args) {
+    switch (spwc) {
+    case 4: k_pixelwise_strip<4, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
+    case 8: k_pixelwise_strip<8, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
+    default: k_pixelwise_strip<FG_TILE_SPW_MAX, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
+    }
+}
+
+// Upper bound on the cell table (prefixes + grains) of one band; larger renders are split into row bands.
+#ifndef FG_TABLE_BYTES_MAX
+#define FG_TABLE_BYTES_MAX ((size_t)48 << 30)
+#endif
+
+// One band [c.row_begin, c.row_end).  returns FG_OK (rendered), 1 (tiled path not applicable), 2 (the
+// cell table of this band does not fit the memory budget: caller splits the band), 3 (the table
+// overflowed: caller uses in-kernel generation) or an error.
+int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
+                     const float* d_offsets, float* d_out, bool staged, uint32_t* d_fbtotal, bool skew_ok) {
+    TilePlan pl = tile_plan(ctx, p, c, n_planes, staged);
+    if (!pl.ok) return 1;
+    const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
+    const size_t n_in = in_stride * n_planes;
+    // cell rectangle of the band: every cell any strip window can touch (+2 cells of slack against
+    // f32-vs-f64 rounding; the kernel re-checks its windows against these bounds)
+    TileCfg g = pl.cfg;
+    {
+        const double iz = 1.0 / (double)p->zoom, dl = p->delta, rmd = p->rm;
+        const double i0 = std::floor((0.5 * iz - (double)c.off_max_x - rmd) / dl) - 2.0;
+        const double i1 = std::floor((((double)p->out_w - 0.5) * iz - (double)c.off_min_x + rmd) / dl) + 2.0;
+        const double j0 = std::floor((((double)c.row_begin + 0.5) * iz - (double)c.off_max_y - rmd) / dl) - 2.0;
+        const double j1 = std::floor((((double)c.row_end - 0.5) * iz - (double)c.off_min_y + rmd) / dl) + 2.0;
+        if (!(i0 > -2.0e9 && i1 < 2.0e9 && j0 > -2.0e9 && j1 < 2.0e9)) return 1;
+        g.bm_i0 = (int)i0; g.bm_j0 = (int)j0;
+        g.bm_cols = (int)(i1 - i0 + 1.0); g.bm_rows = (int)(j1 - j0 + 1.0);
+        g.bm_pitchw = (uint32_t)((g.bm_cols + 31) / 32);
+        g.ppitch = (uint32_t)((g.bm_cols + 1 + 7) / 8 * 8);
+        const float rcl = c.rad.mean_linear > c.rad.rm ? c.rad.rm : c.rad.mean_linear;
+        g.r2c = rcl * rcl;
+    }
+    const size_t bm_plane_words = (size_t)g.bm_rows * g.bm_pitchw;
+    if (bm_plane_words * (size_t)n_planes * 4 > ((size_t)12 << 30) || g.bm_pitchw * 32u / 256u + 1u > 65535u) return 1;
+    const size_t n_rows_all = (size_t)g.bm_rows * n_planes;
+    const size_t pg_bytes = n_rows_all * g.ppitch * 4;
+    if (staged && (pg_bytes > ctx->table_max / 2 || g.bm_rows > 2000000)) return 2;
+    int rc;
+    if ((rc = ensure(ctx, ctx->thr, n_in * 16))) return rc;
+    if ((rc = ensure(ctx, ctx->bitmap, bm_plane_words * (size_t)n_planes * 4))) return rc;
+    const uint32_t units = (uint32_t)g.n_strips * g.n_segs * n_planes;
+    if ((rc = ensure(ctx, ctx->tiles, (size_t)units * sizeof(TileRef) + 64))) return rc;
+    uint64_t* d_thr = (uint64_t*)ctx->thr.p;
+    double* d_e = (double*)((unsigned char*)ctx->thr.p + n_in * 8);
+    uint32_t* d_fbcount = (uint32_t*)ctx->tiles.p;
+    TileRef* d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
+    cudaStream_t s = ctx->stream;
+    FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[6], s)); // ev[6]..ev[4]: thresholds, bitmap, cell table
+    // input rows the band's cell rows map to (clamped like Plane::get_clamped), one row of slack
+    const int iy0 = std::min(std::max((int)std::floor((double)g.bm_j0 * (double)p->delta) - 1, 0), (int)p->in_h - 1);
+    const int iy1 = std::min(std::max((int)std::floor((double)(g.bm_j0 + g.bm_rows) * (double)p->delta) + 1, 0), (int)p->in_h - 1);
+    const size_t thr_first = (size_t)iy0 * p->in_w, thr_n = (size_t)(iy1 - iy0 + 1) * p->in_w;
+    const unsigned tb = (unsigned)std::min<size_t>((thr_n + 255) / 256, (size_t)ctx->sm_count * 16);
+    k_thresholds<<<dim3(tb, (unsigned)n_planes), 256, 0, s>>>(d_lambda, in_stride, thr_first, thr_n, p->delta, d_thr, d_e);
+    FG_CUDA(ctx, cudaGetLastError());
+    uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
+    {
+        dim3 bgrid((unsigned)((g.bm_rows + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
+#define FG_LAUNCH_BM(SD, NPL)                                                                                       \
+    k_first_draw_bitmap<SD, NPL><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, \
+                                                       g.bm_cols, g.bm_rows, g.bm_pitchw, c)
+        if (c.seeding == 0) {
+            if (n_planes == 3) FG_LAUNCH_BM(0, 3);
+            else if (n_planes == 1) FG_LAUNCH_BM(0, 1);
+            else FG_LAUNCH_BM(0, 0);
+        } else {
+            FG_LAUNCH_BM(1, 0);
+        }
+#undef FG_LAUNCH_BM
+        FG_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->stats.launches += 2;
+    CellTable tab{};
+    double table_dens = 0.0;
+    if (staged) {
+        // row capacities from the expected grain counts, then the table itself
+        const size_t s_bytes = align_up((uint32_t)((size_t)n_planes * p->in_h * 8), 256);
+        const size_t base_bytes = (n_rows_all + 1) * 8, cap_bytes = n_rows_all * 4;
+        if ((rc = ensure(ctx, ctx->rowinfo, s_bytes + base_bytes + cap_bytes + 256 + 64))) return rc;
+        if ((rc = ensure(ctx, ctx->ptab, pg_bytes))) {
+            if (rc == FG_ERR_OOM) { ctx->err.clear(); return 2; }
+            return rc;
+        }
+        double* d_S = (double*)ctx->rowinfo.p;
+        uint64_t* d_rowbase = (uint64_t*)((unsigned char*)ctx->rowinfo.p + s_bytes);
+        uint32_t* d_rowcap = (uint32_t*)((unsigned char*)d_rowbase + (base_bytes + 255) / 256 * 256);
+        uint32_t* d_overflow = (uint32_t*)((unsigned char*)d_rowcap + (cap_bytes + 63) / 64 * 64);
+        k_row_expect<<<dim3((unsigned)(iy1 - iy0 + 1), n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, iy0, d_S, c);
+        FG_CUDA(ctx, cudaGetLastError());
+        k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, ctx->table_slack_sigma, d_rowbase, d_rowcap, c);
+        FG_CUDA(ctx, cudaGetLastError());
+        FG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 4, s));
+        uint64_t total = 0;
+        FG_CUDA(ctx, cudaMemcpyAsync(&total, d_rowbase + n_rows_all, 8, cudaMemcpyDeviceToHost, s));
+        FG_CUDA(ctx, cudaStreamSynchronize(s));
+        const size_t bpg = c.rad.lognorm ? 14 : 10;
+        if (total == 0xFFFFFFFFFFFFFFFFULL || total * bpg + pg_bytes > ctx->table_max) return 2;
+        const size_t g_bytes = ((size_t)total * 8 + 255) / 256 * 256;
+        const size_t r2_bytes = c.rad.lognorm ? ((size_t)total * 4 + 255) / 256 * 256 : 0;
+        if ((rc = ensure(ctx, ctx->gtab, g_bytes + r2_bytes + (size_t)total * 2 + 256))) {
+            if (rc == FG_ERR_OOM) { ctx->err.clear(); return 2; }
+            return rc;
+        }
+        float2* d_G = (float2*)ctx->gtab.p;
+        float* d_R2 = (float*)((unsigned char*)ctx->gtab.p + g_bytes);
+        uint16_t* d_C = (uint16_t*)((unsigned char*)ctx->gtab.p + g_bytes + r2_bytes);
+        StageGeo geo{g.bm_i0, g.bm_j0, g.bm_cols, g.bm_rows, g.bm_pitchw, g.ppitch};
+        const unsigned ggrid = (unsigned)((n_rows_all + FG_GW_WARPS - 1) / FG_GW_WARPS);
+        if (c.rad.lognorm)
+            k_gen_rows<true><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
+                                                               d_rowbase, d_rowcap, d_G, d_R2, d_C, d_overflow, geo, n_planes, c);
+        else
+            k_gen_rows<false><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
+                                                                d_rowbase, d_rowcap, d_G, d_R2, d_C, d_overflow, geo, n_planes, c);
+        FG_CUDA(ctx, cudaGetLastError());
+        uint32_t overflow = 0;
+        FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));
+        FG_CUDA(ctx, cudaStreamSynchronize(s));
+        ctx->stats.launches += 3;
+        if (overflow) return 3; // a row outgrew its expected size + 8 sigma (or a cell holds > 65535 grains): regenerate in-kernel instead
+        tab.Pg = (const uint32_t*)ctx->ptab.p;
+        tab.rowbase = d_rowbase;
+        tab.Gg = d_G;
+        tab.R2g = d_R2;
+        tab.Cg = d_C;
+        table_dens = (double)total / ((double)n_rows_all * (double)g.bm_cols);
+    }
+    const float2* off = (const float2*)d_offsets;
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+    SkewPlan sk{};
+    if (staged && skew_ok) sk = skew_plan(ctx, p, c, n_planes, table_dens);
+    uint32_t units_run = units;
+    if (sk.ok) {
+        SkewCfg& k = sk.cfg;
+        k.bm_i0 = g.bm_i0; k.bm_j0 = g.bm_j0; k.bm_cols = g.bm_cols; k.bm_rows = g.bm_rows; k.ppitch = g.ppitch; k.r2c = g.r2c;
+        units_run = (uint32_t)k.n_strips * k.n_segs * n_planes;
+        if (units_run > units) { // the list was sized for the strip kernel's segments
+            if ((rc = ensure(ctx, ctx->tiles, (size_t)units_run * sizeof(TileRef) + 64))) return rc;
+            d_fbcount = (uint32_t*)ctx->tiles.p;
+            d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
+            FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+        }
+        if (sk.spwc == 4) k_pixelwise_skew<4><<<units_run, FG_SK_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
+        else k_pixelwise_skew<8><<<units_run, FG_SK_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
+        g.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
+    } else if (staged) {
+        if (c.rad.lognorm) launch_strip<true, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
+        else launch_strip<false, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
+    } else {
+        if (c.rad.lognorm) launch_strip<true, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
+        else launch_strip<false, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
+    }
+    FG_CUDA(ctx, cudaGetLastError());
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
+    const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);
+    const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units_run * chunks, (uint64_t)ctx->sm_count * 8);
+    if (staged && c.rad.lognorm)
+        k_pixelwise_table_tiles<true><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
+                                                          chunks, d_fbtotal, g, c, tab);
+    else if (staged)
+        k_pixelwise_table_tiles<false><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
+                                                           chunks, d_fbtotal, g, c, tab);
+    else
+        k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
+                                                     chunks, d_fbtotal, c);
+    FG_CUDA(ctx, cudaGetLastError());
+    ctx->stats.launches += 2;
+    if (std::getenv("FG_B200_DEBUG"))
+        std::fprintf(stderr, "[fg] band %d..%d staged=%d TH=%d SEG=%d RH=%d CWB=%d GCAP=%d smem=%u units=%u\n", c.row_begin, c.row_end,
+                     (int)staged, g.TH, g.SEG, g.RH, g.CWB, g.GCAP, g.total, units);
+    ctx->stats.tiles_total += units_run;
+    ctx->strip_launches += 1;
+    ctx->eval_kernel = sk.ok ? "k_pixelwise_skew" : "k_pixelwise_strip";
+    if (std::getenv("FG_B200_DEBUG") && sk.ok)
+        std::fprintf(stderr, "[fg] skew D=%d PS=%d MCAP=%d TCAP=%d R=%d SEG=%d segs=%d smem=%u dens=%.3f\n", sk.cfg.D, sk.cfg.PS, sk.cfg.MCAP, sk.cfg.TCAP, sk.cfg.R,
+                     sk.cfg.SEG, sk.cfg.n_segs, sk.cfg.total, table_dens);
+    return FG_OK;
+}
+
+// returns FG_OK (rendered), 1 (not applicable: caller uses the direct kernel) or an error.
+// path: FG_PATH_AUTO / FG_PATH_STAGED try the cell table first and fall back to in-kernel generation
+// (FG_PATH_TILED) when the table does not fit or a row overflowed.
+int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
+                const float* d_offsets, float* d_out, uint32_t path) {
+    int rc;
+    if ((rc = ensure(ctx, ctx->fbtotal, 64))) return rc;
+    uint32_t* d_fbtotal = (uint32_t*)ctx->fbtotal.p;
+    FG_CUDA(ctx, cudaMemsetAsync(d_fbtotal, 0, 4, ctx->stream));
+    ctx->strip_launches = 0;
+    bool staged = path != FG_PATH_TILED;
+    const bool skew_ok = path != FG_PATH_TILED; // FG_PATH_TILED pins k_pixelwise_strip (tests: an independent second evaluation kernel)
+    rc = tile_render_band(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, staged, d_fbtotal, skew_ok);
+    if (rc == 2 || rc == 3) {
+        // 2: the whole band does not fit one table -> row sub-bands; whatever cannot be staged (and
+        // 3: a table overflow) is rendered with in-kernel generation
+        const int band = c.row_end - c.row_begin;
+        int done = c.row_begin;
+        for (int parts = 2; rc == 2 && parts <= 64 && done == c.row_begin; parts *= 2) {
+            const int rows = (band + parts - 1) / parts;
+            if (rows < 64) break;
+            for (int y = c.row_begin; y < c.row_end; y += rows) {
+                RenderConsts cb = c;
+                cb.row_begin = y;
+                cb.row_end = std::min(y + rows, c.row_end);
+                const int r2 = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, true, d_fbtotal, skew_ok);
+                if (r2 == 1 || r2 == 2 || r2 == 3) break;
+                if (r2) return r2;
+                done = cb.row_end;
+            }
+        }
+        if (done < c.row_end) { // finish (or redo) the rest with in-kernel generation
+            RenderConsts cb = c;
+            cb.row_begin = done;
+            rc = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, false, d_fbtotal, false);
+            if (rc) return rc;
+        }
+        rc = FG_OK;
+    }
+    if (rc) return rc;
+    FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host, d_fbtotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->fb_pending = true;
+    return FG_OK;
+}
+
+} // namespace

@@ -7,7 +7,8 @@
 // colour plane, a CSR table in HBM:
 //
 //   Pg[plane][row][col]   u32, col = 0 .. cols: number of grains of the row's cells [0, col)
-//   Gg[rowbase[plane,row] + Pg[...]]   float2 grain centres in cell order (+ R2g: squared radius, log-normal)
+//   Gg[rowbase[plane,row] + Pg[...]]   float2 grain centres in cell order (+ R2g: squared radius, log-normal;
+//                                      + Cg: the grain's cell column mod 2^16, for k_pixelwise_skew's row merge)
 //
 // so that a strip window is two contiguous slices per cell row and the strip kernel only loads and
 // evaluates.  Row storage is sized from the row's expected grain count (the sum of its cells' Poisson
@@ -116,6 +117,7 @@ struct GenWarpSmem {
     uint64_t q_s0[FG_GW_QCAP], q_s1[FG_GW_QCAP], q_s2[FG_GW_QCAP], q_s3[FG_GW_QCAP], q_dst[FG_GW_QCAP];
     uint32_t q_q[FG_GW_QCAP];
     float q_sx[FG_GW_QCAP];
+    uint16_t q_col[FG_GW_QCAP];
 };
 
 template <bool LOGN>
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
                                                                 const double* __restrict__ e_planes, const float* __restrict__ lambda,
                                                                 size_t in_stride, uint32_t* __restrict__ Pg,
                                                                 const uint64_t* __restrict__ rowbase, const uint32_t* __restrict__ rowcap,
-                                                                float2* __restrict__ Gg, float* __restrict__ R2g,
+                                                                float2* __restrict__ Gg, float* __restrict__ R2g, uint16_t* __restrict__ Cg,
                                                                 uint32_t* __restrict__ overflow, StageGeo geo, int n_planes, RenderConsts c) {
     __shared__ GenWarpSmem sm_all[FG_GW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -152,11 +154,12 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
         }
         return v;
     };
-    auto draw_grains = [&](Xoshiro& rng, float sx, uint64_t dst, uint32_t q) {
+    auto draw_grains = [&](Xoshiro& rng, float sx, uint64_t dst, uint32_t q, uint16_t col) {
         for (uint32_t g = 0; g < q; ++g) {
             const float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
             const float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
             Gg[dst + g] = make_float2(cx, cy);
+            Cg[dst + g] = col; // the grain's cell column in the table (mod 2^16): k_pixelwise_skew merges rows by column
             if (LOGN) { // RadiusProfile::sample + clamp (src/model.rs:137-148, src/pixelwise.rs:89-95)
                 const float radius = radius_sample_clamped(c.rad, rng);
                 R2g[dst + g] = radius > 0.0f ? __fmul_rn(radius, radius) : -1.0f;
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
             if (t < qn) {
                 Xoshiro rng;
                 rng.s0 = sm.q_s0[t]; rng.s1 = sm.q_s1[t]; rng.s2 = sm.q_s2[t]; rng.s3 = sm.q_s3[t];
-                draw_grains(rng, sm.q_sx[t], sm.q_dst[t], sm.q_q[t]);
+                draw_grains(rng, sm.q_sx[t], sm.q_dst[t], sm.q_q[t], sm.q_col[t]);
             }
         }
         qn = 0;
@@ -229,13 +232,15 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
             if (q) sm.cnt[cl] = (uint16_t)q;
             const bool parked = q >= 2u;
             const uint32_t pm = __ballot_sync(0xFFFFFFFFu, parked);
-            if (q == 1u) draw_grains(rng, sx, dst, 1u);
+            const uint16_t col16 = (uint16_t)((uint32_t)tile0 + cl);
+            if (q == 1u) draw_grains(rng, sx, dst, 1u, col16);
             if (parked) {
                 const uint32_t slot = qn + __popc(pm & lt_mask);
                 sm.q_s0[slot] = rng.s0; sm.q_s1[slot] = rng.s1; sm.q_s2[slot] = rng.s2; sm.q_s3[slot] = rng.s3;
                 sm.q_dst[slot] = dst;
                 sm.q_q[slot] = q;
                 sm.q_sx[slot] = sx;
+                sm.q_col[slot] = col16;
             }
             qn += __popc(pm);
             if (qn > FG_GW_QCAP - 32) flush();

@@ -154,6 +154,9 @@ struct TileCfg {
 #define FG_TILE_U3 5    // unrolled grain tests of the merged three-cell-row path
 #endif
 #define FG_TILE_USLOTS 3 // unrolled, predicated grain tests per cell-row range
+#ifndef FG_TILE_UROW
+#define FG_TILE_UROW 2  // staged 3-row path: predicated straight-line tests per cell row (0 = the merged FG_TILE_U3 walk)
+#endif
 
 __device__ __forceinline__ void push_fallback(TileRef* list, uint32_t* count, uint32_t cap, int x0, int y0, int w,
                                               int h, int plane) {
@@ -214,6 +217,57 @@ __device__ __forceinline__ uint64_t pack_f32x2(float x, float y) {
     return r;
 }
 
+// One grain test: if (U < n) dmin = min(dmin, |p - G[ga + U]|^2) -- the un-fused f32 sequence of
+// src/pixelwise.rs:96-98 on the packed pipe.  The LOAD and the MIN are predicated (a lane never loads a grain that is
+// not its own, which keeps the shared-memory wavefronts down); the three arithmetic instructions in between run on
+// whatever `g` holds (the grain just loaded or a stale one) and their result is simply not used by an inactive lane.
+// `g` is a register pair threaded through every third slot: three loads of a sample are in flight at a time, and no
+// register is defined under a predicate only (that would extend its live range to the kernel entry).
+template <int U>
+__device__ __forceinline__ void slot_test(float& dmin, uint64_t& g, uint32_t n, uint32_t ga, uint64_t p) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        ".reg .b64 d, s2;\n\t"
+        ".reg .f32 lo, hi, dd;\n\t"
+        "setp.gt.u32 q, %2, %5;\n\t"
+        "@q ld.shared.b64 %1, [%3+%6];\n\t"
+        "sub.rn.f32x2 d, %4, %1;\n\t"
+        "mul.rn.f32x2 s2, d, d;\n\t"
+        "mov.b64 {lo, hi}, s2;\n\t"
+        "add.rn.f32 dd, lo, hi;\n\t"
+        "@q min.f32 %0, %0, dd;\n\t"
+        "}"
+        : "+f"(dmin), "+l"(g)
+        : "r"(n), "r"(ga), "l"(p), "n"(U), "n"(U * 8));
+}
+template <int U0, int U1>
+struct SlotRun {
+    static __device__ __forceinline__ void run(float& dmin, uint64_t (&g)[3], uint32_t n, uint32_t ga, uint64_t p) {
+        slot_test<U0>(dmin, g[U0 % 3], n, ga, p);
+        SlotRun<U0 + 1, U1>::run(dmin, g, n, ga, p);
+    }
+};
+template <int U1>
+struct SlotRun<U1, U1> {
+    static __device__ __forceinline__ void run(float&, uint64_t (&)[3], uint32_t, uint32_t, uint64_t) {}
+};
+
+// the same for a sample PAIR (A, B) on one cell row each: slots of A and B alternate, each sample has its own two chains
+template <int U0, int U1>
+struct RowSlots {
+    static __device__ __forceinline__ void run(float& dA, float& dB, uint64_t (&chA)[2], uint64_t (&chB)[2], uint32_t nA, uint32_t nB,
+                                               uint32_t gaA, uint32_t gaB, uint64_t pA, uint64_t pB) {
+        slot_test<U0>(dA, chA[U0 & 1], nA, gaA, pA);
+        slot_test<U0>(dB, chB[U0 & 1], nB, gaB, pB);
+        RowSlots<U0 + 1, U1>::run(dA, dB, chA, chB, nA, nB, gaA, gaB, pA, pB);
+    }
+};
+template <int U1>
+struct RowSlots<U1, U1> {
+    static __device__ __forceinline__ void run(float&, float&, uint64_t (&)[2], uint64_t (&)[2], uint32_t, uint32_t, uint32_t, uint32_t, uint64_t, uint64_t) {}
+};
+
 // packed byte offsets of P[row][i0 - i_lo] and P[row][i1 - i_lo + 1] for sample abscissa xg (0 = no cells).
 // Out of line on purpose: two IEEE divisions per call, 16 call sites in the unrolled sample loop.
 __device__ __noinline__ uint32_t col_range_packed(float xg, float rm, float delta, int i_lo) {
@@ -228,6 +282,7 @@ struct CellTable {
     const uint64_t* rowbase;
     const float2* Gg;
     const float* R2g;
+    const uint16_t* Cg; // cell column (mod 2^16) of every grain
 };
 
 template <int SPWC, bool LOGN, bool STAGED>
@@ -707,6 +762,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                 uint32_t wps = (uint32_t)__cvta_generic_to_shared(wp);
                 asm volatile("" : "+r"(Ps), "+r"(Gs), "+r"(wps));
                 const uint32_t PS2 = (uint32_t)PS * 2u, RHPS2 = (uint32_t)RH * PS2;
+                uint64_t chA[2] = {0ull, 0ull}, chB[2] = {0ull, 0ull}; // slot_test load chains (any defined value)
                 if (LOGN) {
                     // per-grain radii: one sample at a time, per cell row FG_TILE_USLOTS predicated tests
                     // against the grain's own r^2, then an early-exit remainder loop
@@ -783,12 +839,47 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                             const uint32_t s1B = lds_u16(o1B + a2B), e1B = lds_u16(o1B + b2B);
                             const uint32_t s2A = lds_u16(o2A + a2A), e2A = lds_u16(o2A + b2A);
                             const uint32_t s2B = lds_u16(o2B + a2B), e2B = lds_u16(o2B + b2B);
+                            const uint64_t pA = pack_f32x2(xgA, ygA), pB = pack_f32x2(xgB, ygB);
+#if FG_TILE_UROW > 0
+                            if (STAGED) {
+                                // Per cell row FG_TILE_UROW straight-line tests whose LOADS are predicated on the row's own
+                                // count (slot_test): immediate-offset addresses, no slot -> row selection, and a lane never
+                                // loads a grain that is not its candidate (fewer shared-memory wavefronts).  What is left of
+                                // the three rows (a few % of the samples) is walked as one list by the early-exit loop below.
+                                const uint32_t n0A = e0A - s0A, n1A = e1A - s1A, n2A = e2A - s2A;
+                                const uint32_t n0B = e0B - s0B, n1B = e1B - s1B, n2B = e2B - s2B;
+                                const uint32_t g0A = Gs + s0A * 8u, g1A = Gs + s1A * 8u, g2A = Gs + s2A * 8u;
+                                const uint32_t g0B = Gs + s0B * 8u, g1B = Gs + s1B * 8u, g2B = Gs + s2B * 8u;
+                                RowSlots<0, FG_TILE_UROW>::run(dminA, dminB, chA, chB, n0A, n0B, g0A, g0B, pA, pB);
+                                RowSlots<0, FG_TILE_UROW>::run(dminA, dminB, chA, chB, n1A, n1B, g1A, g1B, pA, pB);
+                                RowSlots<0, FG_TILE_UROW>::run(dminA, dminB, chA, chB, n2A, n2B, g2A, g2B, pA, pB);
+                                constexpr uint32_t U = FG_TILE_UROW;
+                                if (max(max(n0A, n1A), n2A) > U && !(dminA <= r2)) {
+                                    const uint32_t m0 = n0A > U ? n0A - U : 0u, m1 = m0 + (n1A > U ? n1A - U : 0u), m = m1 + (n2A > U ? n2A - U : 0u);
+                                    const uint32_t b0 = g0A + U * 8u, b1 = g1A + U * 8u - m0 * 8u, b2 = g2A + U * 8u - m1 * 8u;
+                                    uint32_t u = 0;
+                                    do {
+                                        const float d2 = dist2_packed(pA, lds_f32x2((u < m0 ? b0 : (u < m1 ? b1 : b2)) + u * 8u));
+                                        if (d2 <= r2) { dminA = d2; break; }
+                                    } while (++u < m);
+                                }
+                                if (max(max(n0B, n1B), n2B) > U && !(dminB <= r2)) {
+                                    const uint32_t m0 = n0B > U ? n0B - U : 0u, m1 = m0 + (n1B > U ? n1B - U : 0u), m = m1 + (n2B > U ? n2B - U : 0u);
+                                    const uint32_t b0 = g0B + U * 8u, b1 = g1B + U * 8u - m0 * 8u, b2 = g2B + U * 8u - m1 * 8u;
+                                    uint32_t u = 0;
+                                    do {
+                                        const float d2 = dist2_packed(pB, lds_f32x2((u < m0 ? b0 : (u < m1 ? b1 : b2)) + u * 8u));
+                                        if (d2 <= r2) { dminB = d2; break; }
+                                    } while (++u < m);
+                                }
+                            } else
+#endif
+                            {
                             // STAGED rows never wrap inside the ring: end >= start
                             const uint32_t c1A = e0A - s0A + ((!STAGED && e0A < s0A) ? GC : 0u), c1B = e0B - s0B + ((!STAGED && e0B < s0B) ? GC : 0u);
                             const uint32_t c2A = c1A + e1A - s1A + ((!STAGED && e1A < s1A) ? GC : 0u), c2B = c1B + e1B - s1B + ((!STAGED && e1B < s1B) ? GC : 0u);
                             const uint32_t nA = c2A + e2A - s2A + ((!STAGED && e2A < s2A) ? GC : 0u), nB = c2B + e2B - s2B + ((!STAGED && e2B < s2B) ? GC : 0u);
                             const uint32_t t1A = s1A - c1A, t2A = s2A - c2A, t1B = s1B - c1B, t2B = s2B - c2B; // mod 2^32
-                            const uint64_t pA = pack_f32x2(xgA, ygA), pB = pack_f32x2(xgB, ygB);
                             float2 gA[FG_TILE_U3], gB[FG_TILE_U3];
 #pragma unroll
                             for (int u = 0; u < FG_TILE_U3; ++u) { // past n: stale but in-bounds (pad behind the ring)
@@ -820,6 +911,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                                     const float d2 = dist2_packed(pB, lds_f32x2(Gs + gi * 8u));
                                     if (d2 <= r2) { dminB = d2; break; }
                                 } while (++u < nB);
+                            }
                             }
                         } else {
                         const uint32_t nrowA = (a2A != b2A) ? (jpA >> 24) : 0u, nrowB = (a2B != b2B) ? (jpB >> 24) : 0u;
@@ -959,326 +1051,3 @@ __global__ void __launch_bounds__(256) k_pixelwise_table_tiles(const float* __re
 }
 
 } // namespace fg
-
-namespace {
-using namespace fg;
-
-struct TilePlan { TileCfg cfg; int spwc; bool ok; };
-
-inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
-
-// Choose the strip geometry for a render; ok == false -> the tiled path does not apply.
-TilePlan tile_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, bool staged) {
-    TilePlan pl{};
-    pl.ok = false;
-    if (p->n_samples > (1u << 20)) return pl;
-    const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
-    const double ox = (double)c.off_max_x - (double)c.off_min_x, oy = (double)c.off_max_y - (double)c.off_min_y;
-    const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0;
-    if (!(cwb < 2040.0)) return pl;
-    if (!(2.0 * rm / delta + 3.0 < 250.0)) return pl;   // cell rows per sample are packed in 8 bits
-    const int CWB = (int)cwb;
-    const int PS = staged ? (CWB + 8 + 3) / 4 * 4 : CWB + 2; // staged: + column shift (<= 3) + vector tail (<= 3), multiple of 4
-    const int R = std::max(1, std::min(15, FG_TILE_CELLS / (CWB + 1)));
-    const int spwc = p->n_samples <= 4u * FG_TILE_WARPS ? 4 : (p->n_samples <= 8u * FG_TILE_WARPS ? 8 : FG_TILE_SPW_MAX);
-    const int band = c.row_end - c.row_begin;
-    const size_t smem_max = ctx->smem_optin;
-    const uint32_t bpg = c.rad.lognorm ? 12u : 8u;      // bytes per grain: (cx, cy) [+ r^2]
-    // Largest step height whose window fits; the grain ring takes all remaining shared memory.
-    // pass 0 insists that the ring holds the window at a plausible density (0.45 grains per cell;
-    // iid-uniform 8-bit input averages 1/pi); pass 1 takes anything that fits -- denser content
-    // overflows into the fallback list at run time.
-    for (int pass = 0; pass < 2 && !pl.ok; ++pass) {
-        static const int th_candidates[] = {32, 24, 16, 12, 8, 6, 4, 3, 2, 1};
-        static const int th_forced = std::getenv("FG_B200_TH") ? std::atoi(std::getenv("FG_B200_TH")) : 0; // experiments
-        for (int TH : th_candidates) {
-            if (pl.ok) break;
-            if (th_forced > 0 && TH != th_forced) continue;
-            if (TH > 1 && TH > 2 * band) continue;
-            const double rhb = ((TH - 1) * inv_zoom + oy + 2.0 * rm) / delta + 4.0;
-            if (!(rhb < 30000.0)) continue;
-            const int RH = (int)rhb;
-            TileCfg g{};
-            g.TH = TH; g.CWB = CWB; g.RH = RH; g.PS = PS; g.R = R;
-            uint32_t off = 0;
-            g.off_col = off; off = align_up(off + (staged ? 0u : (uint32_t)CWB * 16u), 16);
-            g.off_P = off; off = align_up(off + (uint32_t)(RH + (staged ? 2 : 0)) * PS * 2u, 16);
-            g.off_list = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
-            g.off_E = off; off = align_up(off + (staged ? 0u : (uint32_t)(R * (CWB + 1) + 2) * 2u), 16);
-            g.off_cnt = off; off = align_up(off + (staged ? 0u : (uint32_t)(FG_TILE_NE + 8) * 4u), 16);
-            g.off_rows = off; off = align_up(off + (staged ? (uint32_t)RH * 28u + 16u : 0u), 16);
-            g.off_wtot = off; off = align_up(off + (uint32_t)(FG_TILE_WARPS + 4) * 4u, 16);
-            g.off_pcount = off; off = align_up(off + (uint32_t)TH * 32u * 4u, 16);
-            g.off_wpair = off; off = align_up(off + (uint32_t)FG_TILE_WARPS * TH * spwc * 8u, 16);
-            if ((size_t)off + 64 + (size_t)bpg * (2048 + FG_TILE_GPAD) > smem_max) continue;
-            uint32_t gcap = (uint32_t)((smem_max - off - 64) / bpg) - FG_TILE_GPAD;
-            gcap = std::min<uint32_t>(gcap / 64 * 64, 65472u);
-            if (gcap < 2048) continue;
-            if (pass == 0 && (double)gcap < 0.45 * (double)RH * (double)CWB) continue;
-            g.GCAP = (int)gcap;
-            g.off_G = off; off = align_up(off + (gcap + FG_TILE_GPAD) * 8u, 16);
-            g.off_R2 = off;
-            if (c.rad.lognorm) off = align_up(off + (gcap + FG_TILE_GPAD) * 4u, 16);
-            g.total = off;
-            if (off > smem_max) continue;
-            pl.cfg = g;
-            pl.ok = true;
-        }
-    }
-    if (!pl.ok) return pl;
-    TileCfg& g = pl.cfg;
-    g.n_strips = (int)((p->out_w + 31) / 32);
-    // segment height: maximise (wave efficiency over the SMs) x (1 - start-up share).  A segment
-    // regenerates the cell rows of its first window (RH rows = RH*delta*zoom pixel rows of work).
-    const double startup_rows = (double)g.RH * delta * (double)p->zoom * (staged ? 0.05 : 1.0); // staged: a load, not a generation
-    const long long per_seg_units = (long long)g.n_strips * n_planes;
-    int best_n = 1;
-    double best_eff = -1.0;
-    const int max_n = std::max(1, band / std::max(1, 4 * g.TH));
-    auto seg_eff = [&](int n) {
-        int seg = (band + n - 1) / n;
-        seg = (seg + g.TH - 1) / g.TH * g.TH;
-        const int n_eff = (band + seg - 1) / seg;
-        const double waves = (double)per_seg_units * n_eff / ctx->sm_count;
-        return waves / std::ceil(waves) * ((double)seg / ((double)seg + startup_rows));
-    };
-    for (int n = 1; n <= max_n; ++n) best_eff = std::max(best_eff, seg_eff(n));
-    // among near-optimal splits prefer the finest one: more, shorter CTAs balance content-dependent cost
-    for (int n = 1; n <= max_n; ++n)
-        if (seg_eff(n) >= best_eff - 0.01) best_n = n;
-    int seg = (band + best_n - 1) / best_n;
-    seg = (seg + g.TH - 1) / g.TH * g.TH;
-    g.SEG = seg;
-    g.n_segs = (band + seg - 1) / seg;
-    pl.spwc = spwc;
-    return pl;
-}
-
-template <int SP, bool LG, bool ST>
-cudaError_t strip_attr(int smem) {
-    return cudaFuncSetAttribute(k_pixelwise_strip<SP, LG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-}
-
-int tile_setup(fg_ctx* ctx) {
-    cudaError_t e;
-    const int smem = (int)ctx->smem_optin;
-#define FG_ATTR(SP)                                                                                               \
-    if ((e = strip_attr<SP, false, false>(smem)) != cudaSuccess || (e = strip_attr<SP, true, false>(smem)) != cudaSuccess || \
-        (e = strip_attr<SP, false, true>(smem)) != cudaSuccess || (e = strip_attr<SP, true, true>(smem)) != cudaSuccess)     \
-        return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_strip)");
-    FG_ATTR(4)
-    FG_ATTR(8)
-    FG_ATTR(FG_TILE_SPW_MAX)
-#undef FG_ATTR
-    return FG_OK;
-}
-
-template <bool LG, bool ST, typename... Args>
-void launch_strip(int spwc, uint32_t units, uint32_t smem, cudaStream_t s, Args... args) {
-    switch (spwc) {
-    case 4: k_pixelwise_strip<4, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
-    case 8: k_pixelwise_strip<8, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
-    default: k_pixelwise_strip<FG_TILE_SPW_MAX, LG, ST><<<units, FG_TILE_THREADS, smem, s>>>(args...); break;
-    }
-}
-
-// Upper bound on the cell table (prefixes + grains) of one band; larger renders are split into row bands.
-#ifndef FG_TABLE_BYTES_MAX
-#define FG_TABLE_BYTES_MAX ((size_t)48 << 30)
-#endif
-
-// One band [c.row_begin, c.row_end).  returns FG_OK (rendered), 1 (tiled path not applicable), 2 (the
-// cell table of this band does not fit the memory budget: caller splits the band), 3 (the table
-// overflowed: caller uses in-kernel generation) or an error.
-int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
-                     const float* d_offsets, float* d_out, bool staged, uint32_t* d_fbtotal) {
-    TilePlan pl = tile_plan(ctx, p, c, n_planes, staged);
-    if (!pl.ok) return 1;
-    const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
-    const size_t n_in = in_stride * n_planes;
-    // cell rectangle of the band: every cell any strip window can touch (+2 cells of slack against
-    // f32-vs-f64 rounding; the kernel re-checks its windows against these bounds)
-    TileCfg g = pl.cfg;
-    {
-        const double iz = 1.0 / (double)p->zoom, dl = p->delta, rmd = p->rm;
-        const double i0 = std::floor((0.5 * iz - (double)c.off_max_x - rmd) / dl) - 2.0;
-        const double i1 = std::floor((((double)p->out_w - 0.5) * iz - (double)c.off_min_x + rmd) / dl) + 2.0;
-        const double j0 = std::floor((((double)c.row_begin + 0.5) * iz - (double)c.off_max_y - rmd) / dl) - 2.0;
-        const double j1 = std::floor((((double)c.row_end - 0.5) * iz - (double)c.off_min_y + rmd) / dl) + 2.0;
-        if (!(i0 > -2.0e9 && i1 < 2.0e9 && j0 > -2.0e9 && j1 < 2.0e9)) return 1;
-        g.bm_i0 = (int)i0; g.bm_j0 = (int)j0;
-        g.bm_cols = (int)(i1 - i0 + 1.0); g.bm_rows = (int)(j1 - j0 + 1.0);
-        g.bm_pitchw = (uint32_t)((g.bm_cols + 31) / 32);
-        g.ppitch = (uint32_t)((g.bm_cols + 1 + 7) / 8 * 8);
-        const float rcl = c.rad.mean_linear > c.rad.rm ? c.rad.rm : c.rad.mean_linear;
-        g.r2c = rcl * rcl;
-    }
-    const size_t bm_plane_words = (size_t)g.bm_rows * g.bm_pitchw;
-    if (bm_plane_words * (size_t)n_planes * 4 > ((size_t)12 << 30) || g.bm_pitchw * 32u / 256u + 1u > 65535u) return 1;
-    const size_t n_rows_all = (size_t)g.bm_rows * n_planes;
-    const size_t pg_bytes = n_rows_all * g.ppitch * 4;
-    if (staged && (pg_bytes > ctx->table_max / 2 || g.bm_rows > 2000000)) return 2;
-    int rc;
-    if ((rc = ensure(ctx, ctx->thr, n_in * 16))) return rc;
-    if ((rc = ensure(ctx, ctx->bitmap, bm_plane_words * (size_t)n_planes * 4))) return rc;
-    const uint32_t units = (uint32_t)g.n_strips * g.n_segs * n_planes;
-    if ((rc = ensure(ctx, ctx->tiles, (size_t)units * sizeof(TileRef) + 64))) return rc;
-    uint64_t* d_thr = (uint64_t*)ctx->thr.p;
-    double* d_e = (double*)((unsigned char*)ctx->thr.p + n_in * 8);
-    uint32_t* d_fbcount = (uint32_t*)ctx->tiles.p;
-    TileRef* d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
-    cudaStream_t s = ctx->stream;
-    FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
-    FG_CUDA(ctx, cudaEventRecord(ctx->ev[6], s)); // ev[6]..ev[4]: thresholds, bitmap, cell table
-    // input rows the band's cell rows map to (clamped like Plane::get_clamped), one row of slack
-    const int iy0 = std::min(std::max((int)std::floor((double)g.bm_j0 * (double)p->delta) - 1, 0), (int)p->in_h - 1);
-    const int iy1 = std::min(std::max((int)std::floor((double)(g.bm_j0 + g.bm_rows) * (double)p->delta) + 1, 0), (int)p->in_h - 1);
-    const size_t thr_first = (size_t)iy0 * p->in_w, thr_n = (size_t)(iy1 - iy0 + 1) * p->in_w;
-    const unsigned tb = (unsigned)std::min<size_t>((thr_n + 255) / 256, (size_t)ctx->sm_count * 16);
-    k_thresholds<<<dim3(tb, (unsigned)n_planes), 256, 0, s>>>(d_lambda, in_stride, thr_first, thr_n, p->delta, d_thr, d_e);
-    FG_CUDA(ctx, cudaGetLastError());
-    uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
-    {
-        dim3 bgrid((unsigned)((g.bm_rows + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
-#define FG_LAUNCH_BM(SD, NPL)                                                                                       \
-    k_first_draw_bitmap<SD, NPL><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, \
-                                                       g.bm_cols, g.bm_rows, g.bm_pitchw, c)
-        if (c.seeding == 0) {
-            if (n_planes == 3) FG_LAUNCH_BM(0, 3);
-            else if (n_planes == 1) FG_LAUNCH_BM(0, 1);
-            else FG_LAUNCH_BM(0, 0);
-        } else {
-            FG_LAUNCH_BM(1, 0);
-        }
-#undef FG_LAUNCH_BM
-        FG_CUDA(ctx, cudaGetLastError());
-    }
-    ctx->stats.launches += 2;
-    CellTable tab{};
-    if (staged) {
-        // row capacities from the expected grain counts, then the table itself
-        const size_t s_bytes = align_up((uint32_t)((size_t)n_planes * p->in_h * 8), 256);
-        const size_t base_bytes = (n_rows_all + 1) * 8, cap_bytes = n_rows_all * 4;
-        if ((rc = ensure(ctx, ctx->rowinfo, s_bytes + base_bytes + cap_bytes + 256 + 64))) return rc;
-        if ((rc = ensure(ctx, ctx->ptab, pg_bytes))) {
-            if (rc == FG_ERR_OOM) { ctx->err.clear(); return 2; }
-            return rc;
-        }
-        double* d_S = (double*)ctx->rowinfo.p;
-        uint64_t* d_rowbase = (uint64_t*)((unsigned char*)ctx->rowinfo.p + s_bytes);
-        uint32_t* d_rowcap = (uint32_t*)((unsigned char*)d_rowbase + (base_bytes + 255) / 256 * 256);
-        uint32_t* d_overflow = (uint32_t*)((unsigned char*)d_rowcap + (cap_bytes + 63) / 64 * 64);
-        k_row_expect<<<dim3((unsigned)(iy1 - iy0 + 1), n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, iy0, d_S, c);
-        FG_CUDA(ctx, cudaGetLastError());
-        k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, ctx->table_slack_sigma, d_rowbase, d_rowcap, c);
-        FG_CUDA(ctx, cudaGetLastError());
-        FG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 4, s));
-        uint64_t total = 0;
-        FG_CUDA(ctx, cudaMemcpyAsync(&total, d_rowbase + n_rows_all, 8, cudaMemcpyDeviceToHost, s));
-        FG_CUDA(ctx, cudaStreamSynchronize(s));
-        const size_t bpg = c.rad.lognorm ? 12 : 8;
-        if (total == 0xFFFFFFFFFFFFFFFFULL || total * bpg + pg_bytes > ctx->table_max) return 2;
-        const size_t g_bytes = ((size_t)total * 8 + 255) / 256 * 256;
-        if ((rc = ensure(ctx, ctx->gtab, g_bytes + (c.rad.lognorm ? (size_t)total * 4 : 0) + 256))) {
-            if (rc == FG_ERR_OOM) { ctx->err.clear(); return 2; }
-            return rc;
-        }
-        float2* d_G = (float2*)ctx->gtab.p;
-        float* d_R2 = (float*)((unsigned char*)ctx->gtab.p + g_bytes);
-        StageGeo geo{g.bm_i0, g.bm_j0, g.bm_cols, g.bm_rows, g.bm_pitchw, g.ppitch};
-        const unsigned ggrid = (unsigned)((n_rows_all + FG_GW_WARPS - 1) / FG_GW_WARPS);
-        if (c.rad.lognorm)
-            k_gen_rows<true><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
-                                                               d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, n_planes, c);
-        else
-            k_gen_rows<false><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
-                                                                d_rowbase, d_rowcap, d_G, d_R2, d_overflow, geo, n_planes, c);
-        FG_CUDA(ctx, cudaGetLastError());
-        uint32_t overflow = 0;
-        FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));
-        FG_CUDA(ctx, cudaStreamSynchronize(s));
-        ctx->stats.launches += 3;
-        if (overflow) return 3; // a row outgrew its expected size + 8 sigma (or a cell holds > 65535 grains): regenerate in-kernel instead
-        tab.Pg = (const uint32_t*)ctx->ptab.p;
-        tab.rowbase = d_rowbase;
-        tab.Gg = d_G;
-        tab.R2g = d_R2;
-    }
-    const float2* off = (const float2*)d_offsets;
-    FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-    if (staged) {
-        if (c.rad.lognorm) launch_strip<true, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
-        else launch_strip<false, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
-    } else {
-        if (c.rad.lognorm) launch_strip<true, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
-        else launch_strip<false, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
-    }
-    FG_CUDA(ctx, cudaGetLastError());
-    FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
-    const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);
-    const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units * chunks, (uint64_t)ctx->sm_count * 8);
-    if (staged && c.rad.lognorm)
-        k_pixelwise_table_tiles<true><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
-                                                          chunks, d_fbtotal, g, c, tab);
-    else if (staged)
-        k_pixelwise_table_tiles<false><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
-                                                           chunks, d_fbtotal, g, c, tab);
-    else
-        k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units,
-                                                     chunks, d_fbtotal, c);
-    FG_CUDA(ctx, cudaGetLastError());
-    ctx->stats.launches += 2;
-    if (std::getenv("FG_B200_DEBUG"))
-        std::fprintf(stderr, "[fg] band %d..%d staged=%d TH=%d SEG=%d RH=%d CWB=%d GCAP=%d smem=%u units=%u\n", c.row_begin, c.row_end,
-                     (int)staged, g.TH, g.SEG, g.RH, g.CWB, g.GCAP, g.total, units);
-    ctx->stats.tiles_total += units;
-    ctx->strip_launches += 1;
-    ctx->eval_kernel = "k_pixelwise_strip";
-    return FG_OK;
-}
-
-// returns FG_OK (rendered), 1 (not applicable: caller uses the direct kernel) or an error.
-// path: FG_PATH_AUTO / FG_PATH_STAGED try the cell table first and fall back to in-kernel generation
-// (FG_PATH_TILED) when the table does not fit or a row overflowed.
-int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, const float* d_lambda,
-                const float* d_offsets, float* d_out, uint32_t path) {
-    int rc;
-    if ((rc = ensure(ctx, ctx->fbtotal, 64))) return rc;
-    uint32_t* d_fbtotal = (uint32_t*)ctx->fbtotal.p;
-    FG_CUDA(ctx, cudaMemsetAsync(d_fbtotal, 0, 4, ctx->stream));
-    ctx->strip_launches = 0;
-    bool staged = path != FG_PATH_TILED;
-    rc = tile_render_band(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, staged, d_fbtotal);
-    if (rc == 2 || rc == 3) {
-        // 2: the whole band does not fit one table -> row sub-bands; whatever cannot be staged (and
-        // 3: a table overflow) is rendered with in-kernel generation
-        const int band = c.row_end - c.row_begin;
-        int done = c.row_begin;
-        for (int parts = 2; rc == 2 && parts <= 64 && done == c.row_begin; parts *= 2) {
-            const int rows = (band + parts - 1) / parts;
-            if (rows < 64) break;
-            for (int y = c.row_begin; y < c.row_end; y += rows) {
-                RenderConsts cb = c;
-                cb.row_begin = y;
-                cb.row_end = std::min(y + rows, c.row_end);
-                const int r2 = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, true, d_fbtotal);
-                if (r2 == 1 || r2 == 2 || r2 == 3) break;
-                if (r2) return r2;
-                done = cb.row_end;
-            }
-        }
-        if (done < c.row_end) { // finish (or redo) the rest with in-kernel generation
-            RenderConsts cb = c;
-            cb.row_begin = done;
-            rc = tile_render_band(ctx, p, cb, n_planes, d_lambda, d_offsets, d_out, false, d_fbtotal);
-            if (rc) return rc;
-        }
-        rc = FG_OK;
-    }
-    if (rc) return rc;
-    FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host, d_fbtotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->fb_pending = true;
-    return FG_OK;
-}
-
-} // namespace
