@@ -570,6 +570,38 @@ def main():
                            + ("peer stores into GPU 0's image + barrier" if peer is not None else "NCCL band gather") + "; rank 0: D2H of the image"}
             del pin_in, pin_out
 
+    # ---- N > 1: the same job from ONE process through the C ABI (fg_context_create_multi): what a single-process caller such
+    # as the reference's render() gets from the box.  Rank 0 drives all N GPUs (one host thread + stream per device inside the
+    # library); the other ranks wait at a barrier.  Pinned host planes in and out, copies inside the timed region.
+    if world > 1:
+        dist.barrier()
+        if rank == 0:
+            try:
+                mctx = fg.Context(devices=list(range(world)))
+                pin_lam = torch.from_numpy(np.stack(lam_host)).pin_memory()
+                pin_res = torch.empty((planes, out_h, out_w), dtype=torch.float32).pin_memory()
+                lam_pinned = [pin_lam[c].numpy() for c in range(planes)]
+                host_outs = [pin_res[c].numpy() for c in range(planes)]
+                full_blk = prep.block(None)
+                for _ in range(2):
+                    mctx.render_planes(full_blk, algo, lam_pinned, offsets, host_outs)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    mctx.render_planes(full_blk, algo, lam_pinned, offsets, host_outs)
+                sp_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+                s = mctx.stats()
+                e2e["single_process"] = {
+                    "value": prep.mpx_samples(sp_ms), "unit": "Mpixel*samples/s", "ms_per_step": sp_ms, "devices": world,
+                    "h2d_bytes_per_step": int(s.h2d_bytes), "d2h_bytes_per_step": int(s.d2h_bytes),
+                    "equals_device_image": bool(np.array_equal(host_outs[0], device_image0)),
+                    "call": "one process, fg_context_create_multi over all N devices + fg_render_planes (pinned host planes in / out; "
+                            "row bands, one host thread and stream per device inside the library)"}
+                del pin_lam, pin_res, lam_pinned, host_outs
+                mctx.close()
+            except Exception as e:  # a side measurement never costs the headline line
+                e2e["single_process"] = {"error": repr(e)[:300]}
+        dist.barrier()
+
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(peaks_file)).get("hbm_gbs") if os.path.exists(peaks_file) else 6650.0

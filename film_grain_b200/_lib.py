@@ -65,6 +65,8 @@ ABI = {
     "fg_device_count": (C.c_int, []),
     "fg_error_string": (C.c_char_p, [C.c_int]),
     "fg_context_create": (C.c_int, [_P(_VP), C.c_int]),
+    "fg_context_create_multi": (C.c_int, [_P(_VP), _P(C.c_int), C.c_int]),
+    "fg_context_device_count": (C.c_int, [_VP]),
     "fg_context_destroy": (None, [_VP]),
     "fg_last_error": (C.c_char_p, [_VP]),
     "fg_last_eval_kernel": (C.c_char_p, [_VP]),

@@ -385,6 +385,195 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
     return FG_OK;
 }
 
+
+// ---- single-process multi-device rendering (fg_context_create_multi) --------------------------------------------
+// The path shards into independent output row bands: device g renders the g-th band of the requested
+// rows with the margin cells regenerated locally -- no halo exchange, no collective.  One host thread per device drives
+// that device's own context; the bands meet in the caller's buffer (host entry points: every device copies its band
+// there itself, over its own PCIe link) or in device 0's image (device entry point: peer stores over NVLink).
+void band_of(int g, int n, int r0, int r1, int& b0, int& b1) {
+    const int rows = r1 - r0, base = rows / n, rem = rows % n;
+    b0 = r0 + g * base + std::min(g, rem);
+    b1 = b0 + base + (g < rem ? 1 : 0);
+}
+
+void request_rows(const fg_params* p, int& r0, int& r1) {
+    if (p->row_begin == 0 && p->row_end == 0) { r0 = 0; r1 = (int)p->out_h; }
+    else { r0 = (int)p->row_begin; r1 = (int)p->row_end; }
+}
+
+// run f(g) for every device of the context, one thread each (the calling thread takes device 0); first failure wins
+template <class F>
+int multi_run(fg_ctx* ctx, F&& f) {
+    const int n = (int)ctx->subs.size();
+    std::vector<int> rcs((size_t)n, FG_OK);
+    try {
+        std::vector<std::thread> th;
+        for (int g = 1; g < n; ++g) th.emplace_back([&rcs, &f, g] { rcs[(size_t)g] = f(g); });
+        rcs[0] = f(0);
+        for (auto& t : th) t.join();
+    } catch (const std::exception& e) {
+        return set_err(ctx, FG_ERR_CUDA, std::string("multi-device render: ") + e.what());
+    }
+    fg_stats agg{};
+    for (int g = 0; g < n; ++g) {
+        fg_stats st{};
+        fg_get_stats(ctx->subs[(size_t)g], &st);
+        agg.kernel_ms = std::max(agg.kernel_ms, st.kernel_ms);
+        agg.h2d_ms = std::max(agg.h2d_ms, st.h2d_ms);
+        agg.d2h_ms = std::max(agg.d2h_ms, st.d2h_ms);
+        agg.strip_ms = std::max(agg.strip_ms, st.strip_ms);
+        agg.table_ms = std::max(agg.table_ms, st.table_ms);
+        agg.strip_launches = std::max(agg.strip_launches, st.strip_launches);
+        agg.launches += st.launches;
+        agg.tiles_total += st.tiles_total;
+        agg.tiles_fallback += st.tiles_fallback;
+        agg.h2d_bytes += st.h2d_bytes;
+        agg.d2h_bytes += st.d2h_bytes;
+    }
+    ctx->stats = agg;
+    for (int g = 0; g < n; ++g)
+        if (rcs[(size_t)g]) {
+            ctx->err = "device " + std::to_string(ctx->subs[(size_t)g]->device) + ": " + ctx->subs[(size_t)g]->err;
+            return rcs[(size_t)g];
+        }
+    return FG_OK;
+}
+
+int multi_render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
+                             const float* offsets, float* const* out, const volatile int* cancel) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    int r0, r1;
+    request_rows(p, r0, r1);
+    const int n = (int)ctx->subs.size();
+    return multi_run(ctx, [&](int g) -> int {
+        fg_params pb = *p;
+        int b0, b1;
+        band_of(g, n, r0, r1, b0, b1);
+        if (b0 >= b1) return FG_OK; // more devices than rows
+        pb.row_begin = (uint32_t)b0;
+        pb.row_end = (uint32_t)b1;
+        return render_planes_host(ctx->subs[(size_t)g], &pb, algo, n_planes, lambda, offsets, out,
+                                  cancel ? cancel : ctx->cancel);
+    });
+}
+
+int multi_render_rgb8_host(fg_ctx* ctx, const fg_params* p, int algo, int color_mode, const uint8_t* rgb_in,
+                           const float* offsets, uint8_t* rgb_out) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    int r0, r1;
+    request_rows(p, r0, r1);
+    const int n = (int)ctx->subs.size();
+    return multi_run(ctx, [&](int g) -> int {
+        fg_params pb = *p;
+        int b0, b1;
+        band_of(g, n, r0, r1, b0, b1);
+        if (b0 >= b1) return FG_OK;
+        pb.row_begin = (uint32_t)b0;
+        pb.row_end = (uint32_t)b1;
+        return fg_render_rgb8(ctx->subs[(size_t)g], &pb, algo, color_mode, rgb_in, offsets, rgb_out);
+    });
+}
+
+// Device-resident planes: d_lambda / d_offsets / d_out live on device 0 (subs[0]).  Device g > 0 pulls the lambda rows its
+// band reads over NVLink (cudaMemcpyPeerAsync into its own pool) and its kernels store their band rows straight into
+// device 0's image through the peer mapping enabled at context creation (a staged peer copy where that is unavailable).
+// subs[0]'s stream waits for every other device, so "the image is complete" is an ordinary stream-order fact for the caller.
+int multi_render_planes_device(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* d_lambda,
+                               const float* d_offsets, float* d_out, int stream_sync) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    if (algo != FG_ALGO_PIXEL && algo != FG_ALGO_GRAIN) return set_err(ctx, FG_ERR_INVALID, "algo must be FG_ALGO_PIXEL or FG_ALGO_GRAIN");
+    if (n_planes < 1 || n_planes > 16) return set_err(ctx, FG_ERR_INVALID, "n_planes must be in 1..16");
+    if (!d_lambda || !d_offsets || !d_out) return set_err(ctx, FG_ERR_INVALID, "NULL buffer");
+    fg_ctx* c0 = ctx->subs[0];
+    std::vector<float> off((size_t)p->n_samples * 2);
+    {
+        ScopedDevice dev(c0->device);
+        FG_CUDA(ctx, cudaMemcpyAsync(off.data(), d_offsets, off.size() * sizeof(float), cudaMemcpyDeviceToHost, c0->stream));
+        FG_CUDA(ctx, cudaEventRecord(c0->ev[7], c0->stream)); // the inputs are ready on device 0 from here on
+        FG_CUDA(ctx, cudaStreamSynchronize(c0->stream));
+    }
+    if ((rc = check_offsets(ctx, p, off.data()))) return rc;
+    int r0, r1;
+    request_rows(p, r0, r1);
+    const int n = (int)ctx->subs.size();
+    const size_t in_elems = (size_t)p->in_w * p->in_h, out_elems = (size_t)p->out_w * p->out_h;
+    rc = multi_run(ctx, [&](int g) -> int {
+        fg_ctx* sc = ctx->subs[(size_t)g];
+        std::lock_guard<std::mutex> sub_lock(sc->mu);
+        ScopedDevice dev(sc->device);
+        sc->err.clear();
+        sc->stats = fg_stats{};
+        sc->fb_pending = false;
+        fg_params pb = *p;
+        int b0, b1;
+        band_of(g, n, r0, r1, b0, b1);
+        if (b0 >= b1) return FG_OK;
+        pb.row_begin = (uint32_t)b0;
+        pb.row_end = (uint32_t)b1;
+        RenderConsts c = make_consts(&pb, off.data());
+        cudaStream_t s = sc->stream;
+        const float* lam = d_lambda;
+        const float* offs = d_offsets;
+        float* dst = d_out;
+        int rcg;
+        if (g > 0) {
+            FG_CUDA(sc, cudaStreamWaitEvent(s, c0->ev[7], 0));
+            if ((rcg = ensure(sc, sc->lambda, in_elems * n_planes * sizeof(float)))) return rcg;
+            if ((rcg = ensure(sc, sc->offsets, off.size() * sizeof(float)))) return rcg;
+            int in_r0, in_r1;
+            input_rows_of_band(&pb, c, algo, in_r0, in_r1);
+            const size_t up_off = (size_t)in_r0 * p->in_w, up_elems = (size_t)(in_r1 - in_r0) * p->in_w;
+            for (int pl = 0; pl < n_planes; ++pl)
+                FG_CUDA(sc, cudaMemcpyPeerAsync((float*)sc->lambda.p + in_elems * pl + up_off, sc->device, d_lambda + in_elems * pl + up_off,
+                                                c0->device, up_elems * sizeof(float), s));
+            FG_CUDA(sc, cudaMemcpyAsync(sc->offsets.p, off.data(), off.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+            lam = (const float*)sc->lambda.p;
+            offs = (const float*)sc->offsets.p;
+            if (!ctx->peer[(size_t)g]) { // no peer mapping: render locally, then a peer copy of the band
+                if ((rcg = ensure(sc, sc->out, out_elems * n_planes * sizeof(float)))) return rcg;
+                dst = (float*)sc->out.p;
+            }
+        }
+        FG_CUDA(sc, cudaEventRecord(sc->ev[1], s));
+        rcg = render_planes_device_locked(sc, &pb, c, algo, n_planes, lam, offs, dst);
+        if (rcg) { cudaStreamSynchronize(s); return rcg; }
+        FG_CUDA(sc, cudaEventRecord(sc->ev[2], s));
+        if (g > 0 && !ctx->peer[(size_t)g]) {
+            const size_t band_off = (size_t)b0 * p->out_w, band_elems = (size_t)(b1 - b0) * p->out_w;
+            for (int pl = 0; pl < n_planes; ++pl)
+                FG_CUDA(sc, cudaMemcpyPeerAsync(d_out + out_elems * pl + band_off, c0->device, dst + out_elems * pl + band_off, sc->device,
+                                                band_elems * sizeof(float), s));
+        }
+        FG_CUDA(sc, cudaEventRecord(sc->ev[8], s));
+        return FG_OK;
+    });
+    if (rc) return rc;
+    {
+        ScopedDevice dev(c0->device);
+        for (int g = 1; g < n; ++g) FG_CUDA(ctx, cudaStreamWaitEvent(c0->stream, ctx->subs[(size_t)g]->ev[8], 0));
+        if (stream_sync) {
+            FG_CUDA(ctx, cudaStreamSynchronize(c0->stream));
+            for (int g = 0; g < n; ++g) {
+                float ms = 0.0f;
+                if (cudaEventElapsedTime(&ms, ctx->subs[(size_t)g]->ev[1], ctx->subs[(size_t)g]->ev[2]) == cudaSuccess)
+                    ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, ms);
+                else cudaGetLastError();
+            }
+        }
+    }
+    return FG_OK;
+}
+
 } // namespace
 
 // ------------------------------------------------------------------------------- ABI
@@ -453,8 +642,46 @@ int fg_context_create(fg_ctx** out, int device) {
     return FG_OK;
 }
 
+int fg_context_create_multi(fg_ctx** out, const int* devices, int n_devices) {
+    if (!out) return FG_ERR_INVALID;
+    *out = nullptr;
+    if (!devices || n_devices < 1 || n_devices > 64) return FG_ERR_INVALID;
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = a + 1; b < n_devices; ++b)
+            if (devices[a] == devices[b]) return FG_ERR_INVALID;
+    fg_ctx* ctx = new (std::nothrow) fg_ctx();
+    if (!ctx) return FG_ERR_OOM;
+    ctx->device = devices[0];
+    for (int g = 0; g < n_devices; ++g) {
+        fg_ctx* sc = nullptr;
+        const int rc = fg_context_create(&sc, devices[g]);
+        if (rc) { fg_context_destroy(ctx); return rc; }
+        ctx->subs.push_back(sc);
+        char ok = 1;
+        if (g > 0) { // let device g store into device 0's memory (NVLink / NVSwitch peer mapping)
+            ScopedDevice dev(devices[g]);
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[g], devices[0]) != cudaSuccess || !can) ok = 0;
+            else {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+            }
+            cudaGetLastError();
+        }
+        ctx->peer.push_back(ok);
+    }
+    ctx->sm_count = ctx->subs[0]->sm_count;
+    *out = ctx;
+    return FG_OK;
+}
+
 void fg_context_destroy(fg_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->subs.empty()) { // multi-device router: owns nothing but its sub-contexts
+        for (fg_ctx* sc : ctx->subs) fg_context_destroy(sc);
+        delete ctx;
+        return;
+    }
     {
         ScopedDevice dev(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
@@ -469,11 +696,17 @@ void fg_context_destroy(fg_ctx* ctx) {
 }
 
 const char* fg_last_error(const fg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-const char* fg_last_eval_kernel(const fg_ctx* ctx) { return ctx ? ctx->eval_kernel : ""; }
-void fg_set_cancel_flag(fg_ctx* ctx, const volatile int* flag) { if (ctx) ctx->cancel = flag; }
+const char* fg_last_eval_kernel(const fg_ctx* ctx) { return ctx ? (ctx->subs.empty() ? ctx->eval_kernel : ctx->subs[0]->eval_kernel) : ""; }
+int fg_context_device_count(const fg_ctx* ctx) { return ctx ? (ctx->subs.empty() ? 1 : (int)ctx->subs.size()) : 0; }
+void fg_set_cancel_flag(fg_ctx* ctx, const volatile int* flag) {
+    if (!ctx) return;
+    ctx->cancel = flag;
+    for (fg_ctx* sc : ctx->subs) sc->cancel = flag;
+}
 void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
     if (!ctx || !out) return;
     *out = ctx->stats;
+    if (!ctx->subs.empty()) return; // aggregated over the devices by the render call
     if (ctx->fb_pending) { // meaningful once the stream is synchronised
         out->tiles_fallback = ctx->fb_count_host;
         out->strip_launches = ctx->strip_launches;
@@ -484,10 +717,20 @@ void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
         else cudaGetLastError();
     }
 }
-uint64_t fg_context_stream(const fg_ctx* ctx) { return ctx ? (uint64_t)(uintptr_t)ctx->stream : 0; }
+uint64_t fg_context_stream(const fg_ctx* ctx) {
+    if (!ctx) return 0;
+    return (uint64_t)(uintptr_t)(ctx->subs.empty() ? ctx->stream : ctx->subs[0]->stream); // multi: device 0's stream
+}
 
 int fg_context_synchronize(fg_ctx* ctx) {
     if (!ctx) return FG_ERR_INVALID;
+    if (!ctx->subs.empty()) {
+        for (fg_ctx* sc : ctx->subs) {
+            const int rc = fg_context_synchronize(sc);
+            if (rc) { ctx->err = sc->err; return rc; }
+        }
+        return FG_OK;
+    }
     ScopedDevice dev(ctx->device);
     FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return FG_OK;
@@ -496,28 +739,31 @@ int fg_context_synchronize(fg_ctx* ctx) {
 int fg_render_pixelwise(fg_ctx* ctx, const fg_params* p, const float* lambda, const float* offsets_input, float* out) {
     const float* lp[1] = {lambda};
     float* op[1] = {out};
-    return render_planes_host(ctx, p, FG_ALGO_PIXEL, 1, lp, offsets_input, op);
+    return fg_render_planes(ctx, p, FG_ALGO_PIXEL, 1, lp, offsets_input, op);
 }
 
 int fg_render_grainwise(fg_ctx* ctx, const fg_params* p, const float* lambda, const float* offsets, float* out) {
     const float* lp[1] = {lambda};
     float* op[1] = {out};
-    return render_planes_host(ctx, p, FG_ALGO_GRAIN, 1, lp, offsets, op);
+    return fg_render_planes(ctx, p, FG_ALGO_GRAIN, 1, lp, offsets, op);
 }
 
 int fg_render_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
                      const float* offsets, float* const* out) {
+    if (ctx && !ctx->subs.empty()) return multi_render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out, nullptr);
     return render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out);
 }
 
 int fg_render_planes_cancelable(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
                                 const float* offsets, float* const* out, const volatile int* cancel) {
+    if (ctx && !ctx->subs.empty()) return multi_render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out, cancel);
     return render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out, cancel);
 }
 
 int fg_render_planes_device(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* d_lambda,
                             const float* d_offsets, float* d_out, int stream_sync) {
     if (!ctx) return FG_ERR_INVALID;
+    if (!ctx->subs.empty()) return multi_render_planes_device(ctx, p, algo, n_planes, d_lambda, d_offsets, d_out, stream_sync);
     std::lock_guard<std::mutex> lock(ctx->mu);
     ScopedDevice dev(ctx->device);
     ctx->err.clear();
@@ -548,6 +794,7 @@ int fg_render_planes_device(fg_ctx* ctx, const fg_params* p, int algo, int n_pla
 int fg_render_rgb8(fg_ctx* ctx, const fg_params* p, int algo, int color_mode, const uint8_t* rgb_in,
                    const float* offsets, uint8_t* rgb_out) {
     if (!ctx) return FG_ERR_INVALID;
+    if (!ctx->subs.empty()) return multi_render_rgb8_host(ctx, p, algo, color_mode, rgb_in, offsets, rgb_out);
     std::lock_guard<std::mutex> lock(ctx->mu);
     ScopedDevice dev(ctx->device);
     ctx->err.clear();
@@ -610,6 +857,7 @@ int fg_dump_cells(fg_ctx* ctx, const fg_params* p, int stream_kind, const int32_
 
 int fg_measure_issue_peak(fg_ctx* ctx, double out[4]) {
     if (!ctx || !out) return FG_ERR_INVALID;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];
     std::lock_guard<std::mutex> lock(ctx->mu);
     ScopedDevice dev(ctx->device);
     ctx->err.clear();

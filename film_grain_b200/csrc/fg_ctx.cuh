@@ -9,6 +9,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -26,7 +27,7 @@ struct DevBuf {
 struct fg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[7] = {};
+    cudaEvent_t ev[9] = {}; // [0..6] timings of a render, [7] / [8] start / done markers of a multi-device render
     std::mutex mu;
     std::string err;
     const volatile int* cancel = nullptr;      // fg_set_cancel_flag: stays until replaced
@@ -42,7 +43,11 @@ struct fg_ctx {
     size_t table_max = (size_t)48 << 30; // cell-table budget per band (FG_B200_TABLE_MAX_BYTES overrides; tests)
     double table_slack_sigma = 8.0; // row capacity = expected grains + this many sigma + 64 (FG_B200_TABLE_SLACK_SIGMA: tests)
     const char* eval_kernel = ""; // name of the kernel that evaluated / rasterised the last render (fg_last_eval_kernel)
-    uint32_t strip_launches = 0; // strip-kernel launches of the last pixel-wise render (row sub-bands)
+    uint32_t strip_launches = 0;
+    // multi-device context (fg_context_create_multi): this object only routes; subs[g] is a complete context on its own
+    // device, subs[0] on the device that owns device-resident inputs and outputs.  peer[g]: device g can store into subs[0]'s memory.
+    std::vector<fg_ctx*> subs;
+    std::vector<char> peer; // strip-kernel launches of the last pixel-wise render (row sub-bands)
 };
 
 namespace {

@@ -32,14 +32,23 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
 class Context:
     """GpuContext (src/wgpu/mod.rs:40-49): owns the device stream and buffer pools."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
+        """device: one CUDA ordinal; devices=[d0, d1, ...]: one context over several devices of the box (row bands,
+        fg_context_create_multi; device-resident buffers live on d0)."""
         self._lib = _lib.load()
         h = C.c_void_p()
-        rc = self._lib.fg_context_create(C.byref(h), device)
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self._lib.fg_context_create_multi(C.byref(h), arr, len(devices))
+            device = devices[0] if devices else 0
+        else:
+            rc = self._lib.fg_context_create(C.byref(h), device)
         if rc != 0:
             raise GpuError(rc, "no usable CUDA device" if rc == _lib.FG_ERR_NO_DEVICE else "context creation failed")
         self._h = h
         self.device = device
+        self.devices = devices if devices is not None else [device]
 
     def close(self):
         if getattr(self, "_h", None):
@@ -51,6 +60,9 @@ class Context:
         that wrapped the context's stream in another runtime's stream object: that runtime may still record
         events on the stream while it tears down, after this object is gone."""
         self._h = None
+
+    def device_count(self) -> int:
+        return int(self._lib.fg_context_device_count(self._h))
 
     def eval_kernel_name(self) -> str:
         return self._lib.fg_last_eval_kernel(self._h).decode()

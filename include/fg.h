@@ -112,6 +112,16 @@ const char* fg_error_string(int code);
 /* Create a context on CUDA device `device` (ordinal).  Allocates a stream and lazily-grown
  * device buffer pools.  Replaces wgpu::context() (src/wgpu/mod.rs:84-86). */
 int fg_context_create(fg_ctx** out, int device);
+/* One context over SEVERAL devices of the box, for the reference's single-process caller (src/lib.rs:141-163,
+ * src/main.rs:60): every render call on it splits the requested output rows into n_devices contiguous row bands, one
+ * host thread and one stream per device; a band's margin cells are regenerated locally (no halo exchange, no
+ * collective).  Host entry points: each device uploads the input rows its band reads and delivers its band into the
+ * caller's buffer over its own PCIe link.  fg_render_planes_device: inputs and output live on devices[0]; the other
+ * devices pull their lambda rows and store their band rows into devices[0]'s image over NVLink (peer access is
+ * enabled here).  Results are bit-identical to a single-device context.  fg_render_rgb8_device, fg_dump_cells and
+ * fg_measure_issue_peak run on devices[0]. */
+int fg_context_create_multi(fg_ctx** out, const int* devices, int n_devices);
+int fg_context_device_count(const fg_ctx* ctx); /* devices a context renders on (1 for fg_context_create) */
 void fg_context_destroy(fg_ctx* ctx);
 /* Last error text of this context (valid until the next call on it); "" if none. */
 const char* fg_last_error(const fg_ctx* ctx);

@@ -457,6 +457,82 @@ def test_full_size_config2_three_plane_render_against_the_oracle(ctx):
             assert bad.size == 0, f"plane {c} rows {a}..{b}: {bad.size} px differ"
 
 
+def _multi_devices():
+    import film_grain_b200 as fg
+    n = fg.device_count()
+    return list(range(min(n, 4))) if n >= 2 else [0]
+
+
+@pytest.mark.parametrize("algo", ["pixel", "grain"])
+def test_single_process_multi_device_context_equals_single_device(ctx, algo):
+    """fg_context_create_multi (the reference's caller is ONE process, src/lib.rs:141-163): a context over several devices
+    splits every render into row bands, one host thread per device.  Host planes (pageable and pinned), a row-band request,
+    the u8 pipeline and the device-pointer entry point (bands stored into device 0's image) all reproduce the single-device
+    render bit for bit.  On a one-GPU box the same code runs with the single device [0] (routing, band arithmetic, stats)."""
+    import torch
+
+    import film_grain_b200 as fg
+    devs = _multi_devices()
+    w, h = 230, 170
+    if algo == "pixel":
+        p = O.make_params(radius=0.1, n_samples=24, algo=O.ALGO_PIXEL)
+    else:
+        p = O.make_params(radius=0.5, n_samples=40, algo=O.ALGO_GRAIN)
+    d, off, off_in = O.derive_common(p, w, h)
+    offs = off_in if algo == "pixel" else off
+    a = O.ALGO_PIXEL if algo == "pixel" else O.ALGO_GRAIN
+    img = noise_u8(w, h, seed=21)
+    lams = [lambda_from_u8(img[:, :, c], d.inv_e_pi_r2) for c in range(3)]
+    ref = ctx.render_planes(fg_params_from(p, d), a, lams, offs)
+    oracle0 = O.render_pixelwise(lams[0], p, d, off_in) if algo == "pixel" else O.render_grainwise(lams[0], p, d, off)
+    assert np.array_equal(ref[0], oracle0)
+    with fg.Context(devices=devs) as mctx:
+        assert mctx.device_count() == len(devs)
+        got = mctx.render_planes(fg_params_from(p, d), a, lams, offs)
+        st = mctx.stats()
+        for c in range(3):
+            assert np.array_equal(got[c], ref[c])
+        assert st.launches > 0 and st.d2h_bytes == 3 * d.output_height * d.output_width * 4
+        one = mctx.render_pixelwise(fg_params_from(p, d), lams[1], offs) if algo == "pixel" else mctx.render_grainwise(fg_params_from(p, d), lams[1], offs)
+        assert np.array_equal(one, ref[1])
+        # a row-band request is split again; rows outside stay untouched
+        pin = torch.full((3, d.output_height, d.output_width), -7.0, dtype=torch.float32).pin_memory()
+        outs = [pin[c].numpy() for c in range(3)]
+        rows = (31, 149)
+        mctx.render_planes(fg_params_from(p, d, rows=rows), a, lams, offs, outs)
+        for c in range(3):
+            assert np.array_equal(outs[c][rows[0]:rows[1]], ref[c][rows[0]:rows[1]])
+            assert np.all(outs[c][:rows[0]] == -7.0) and np.all(outs[c][rows[1]:] == -7.0)
+        # device-resident planes on devices[0]: the other devices store their bands into its image
+        dev0 = torch.device("cuda", devs[0])
+        d_lam = torch.from_numpy(np.stack(lams)).to(dev0)
+        d_off = torch.from_numpy(np.ascontiguousarray(offs)).to(dev0)
+        d_out = torch.full((3, d.output_height, d.output_width), -1.0, dtype=torch.float32, device=dev0)
+        torch.cuda.synchronize(dev0)
+        mctx.render_planes_device(fg_params_from(p, d), a, 3, d_lam.data_ptr(), d_off.data_ptr(), d_out.data_ptr(), sync=True)
+        res = d_out.cpu().numpy()
+        for c in range(3):
+            assert np.array_equal(res[c], ref[c])
+        if algo == "pixel":
+            ref8 = ctx.render_rgb8(fg_params_from(p, d), a, 1, img, offs)
+            got8 = mctx.render_rgb8(fg_params_from(p, d), a, 1, img, offs)
+            assert np.array_equal(got8, ref8)
+        del d_lam, d_off, d_out
+
+
+def test_multi_device_context_rejects_bad_device_lists():
+    import ctypes as C2
+
+    import film_grain_b200 as fg
+    from film_grain_b200 import _lib
+    lib = _lib.load()
+    h = C2.c_void_p()
+    assert lib.fg_context_create_multi(C2.byref(h), (C2.c_int * 2)(0, 0), 2) == _lib.FG_ERR_INVALID  # duplicate
+    assert lib.fg_context_create_multi(C2.byref(h), (C2.c_int * 1)(fg.device_count()), 1) == _lib.FG_ERR_NO_DEVICE
+    assert lib.fg_context_create_multi(C2.byref(h), None, 0) == _lib.FG_ERR_INVALID
+    assert not h.value
+
+
 def test_multi_gpu_bands_into_peer_image_equal_single_gpu_render():
     """N > 1 (needs >= 2 GPUs, skipped otherwise): every rank renders its row band straight into GPU 0's
     peer-mapped image over NVLink (film_grain_b200/dist.py PeerImage) and, separately, through the NCCL
