@@ -4,6 +4,7 @@
 // and the split of a render into row sub-bands (table budget, cancellation points).  Host code only.
 #pragma once
 #include "fg_skew.cuh"
+#include "fg_tri.cuh"
 
 namespace {
 using namespace fg;
@@ -195,6 +196,107 @@ SkewPlan skew_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c,
     return pl;
 }
 
+
+struct TriPlan { TriCfg cfg; int spw; bool ok; };
+
+// Geometry of k_pixelwise_tri for a render; ok == false -> another evaluation kernel.  `dens` = grains per cell of the
+// band's table (its capacity, i.e. expectation + slack): the merged ring must hold the window of a step plus the rows
+// being merged with room for local fluctuations (denser strips go through the fallback list at run time).
+TriPlan tri_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, double dens) {
+    TriPlan pl{};
+    pl.ok = false;
+    static const bool enabled = std::getenv("FG_B200_TRI") && std::atoi(std::getenv("FG_B200_TRI")) != 0; // work in progress: slower than k_pixelwise_strip at C2
+    if (!enabled || c.rad.lognorm || p->rm != p->delta || p->n_samples > 8u * FG_TRI_WARPS || p->n_samples == 0) return pl;
+    const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
+    const double ox = (double)c.off_max_x - (double)c.off_min_x;
+    const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0 + 3.0; // + alignment shift
+    if (!(cwb < 2000.0)) return pl;
+    const int CWB = (int)cwb;
+    const int PS = (CWB + 1 + 7) / 8 * 8;
+    const double cpr = inv_zoom / delta; // cell rows per output pixel row
+    if (!(cpr > 0.05 && cpr < 24.0)) return pl;
+    const int spw = p->n_samples <= 2u * FG_TRI_WARPS ? 2 : (p->n_samples <= 4u * FG_TRI_WARPS ? 4 : 8);
+    const int band = c.row_end - c.row_begin;
+    const int skrange = (int)std::nearbyint((double)c.off_max_y * (double)p->zoom) - (int)std::nearbyint((double)c.off_min_y * (double)p->zoom);
+    if (skrange < 0 || skrange > 200) return pl;
+    const size_t smem_max = ctx->smem_optin;
+    static const int m_forced = std::getenv("FG_B200_TRI_M") ? std::atoi(std::getenv("FG_B200_TRI_M")) : 0; // experiments
+    static const int m_candidates[] = {16, 12, 8, 6, 4, 3, 2, 1};
+    for (int m : m_candidates) {
+        if (m_forced > 0 && m != m_forced) continue;
+        if (m * spw > 32) continue;
+        if (m > 1 && m * cpr < 1.0 - 1e-9) { /* fine: larger steps */ }
+        const int A = (int)std::ceil(m * cpr - 1e-9);
+        if (A < 1 && m < 16) continue; // at least one cell row per step
+        TriCfg g{};
+        g.m = m;
+        g.AMAX = A + 1;
+        g.D = A + 4;
+        g.NG = g.AMAX + 2;
+        if (g.NG > 32) continue;
+        g.NQ = g.D + g.AMAX;
+        g.CWB = CWB;
+        g.PS = PS;
+        int RH = 4;
+        while (RH < 2 * m + skrange + 2) RH <<= 1;
+        g.RH = RH;
+        g.NB = std::max(1, 32 / (m * spw));
+        const double row_grains = (double)CWB * dens; // of one source row's window
+        g.GS = (int)align_up((uint32_t)(g.NG * (row_grains * 1.7 + 16.0) * 10.0) + 512u, 128);
+        uint32_t off = 0;
+        g.off_zq = off; off = align_up(off + (uint32_t)PS * 2u, 128);
+        g.off_zp = off; off = align_up(off + (uint32_t)PS * 4u, 128);
+        g.off_praw = off; off = align_up(off + (uint32_t)g.NG * PS * 4u, 128);
+        g.off_gs = off; off = align_up(off + (uint32_t)g.GS, 128);
+        g.off_sinfo = off; off = align_up(off + (uint32_t)g.NG * 32u, 128);
+        g.off_ext = off; off = align_up(off + 2u * (uint32_t)g.NG * 16u, 128);
+        g.off_minfo = off; off = align_up(off + (uint32_t)g.NQ * 4u, 128);
+        g.off_state = off; off = align_up(off + 64u, 128);
+        g.off_items = off; off = align_up(off + (uint32_t)FG_TRI_WARPS * 512u, 128);
+        g.off_hb = off; off = align_up(off + (uint32_t)(RH + 1) * 32u * spw * 4u, 128);
+        g.off_Q = off; off = align_up(off + (uint32_t)g.NQ * PS * 2u, 128);
+        if ((size_t)off + 8u * 1024u > smem_max) continue;
+        uint32_t mcap = (uint32_t)((smem_max - off) / 8u);
+        mcap = std::min<uint32_t>(mcap, 65000u);
+        // live rows: the window, the rows being merged, and the row a wrap leaves unused at the end of the ring
+        const double need = 3.0 * row_grains * (double)(g.NQ + 1);
+        if (std::getenv("FG_B200_DEBUG"))
+            std::fprintf(stderr, "[fg] tri_plan m=%d spw=%d A=%d NQ=%d PS=%d GS=%d RH=%d fixed=%u mcap=%u need=%.0f dens=%.3f\n", m, spw, A, g.NQ, PS, g.GS, RH, off, mcap, need, dens);
+        if ((double)mcap < 1.3 * need + 128.0) continue;
+        g.MCAP = (int)mcap;
+        g.off_M = off; off += mcap * 8u;
+        g.total = off;
+        if (off > smem_max) continue;
+        // segment height: wave efficiency x (1 - ramp share)
+        g.n_strips = (int)((p->out_w + 31) / 32);
+        const long long per_seg_units = (long long)g.n_strips * n_planes;
+        const double startup_rows = 0.5 * skrange + 3.0 * m;
+        int best_n = 1;
+        double best_eff = -1.0;
+        const int max_n = std::max(1, band / std::max(8, 4 * m));
+        auto seg_of = [&](int n) { return (band + n - 1) / n; };
+        auto seg_eff = [&](int n) {
+            const int seg = seg_of(n);
+            const int n_eff = (band + seg - 1) / seg;
+            const double waves = (double)per_seg_units * n_eff / ctx->sm_count;
+            return waves / std::ceil(waves) * ((double)seg / ((double)seg + startup_rows));
+        };
+        for (int n = 1; n <= max_n; ++n) best_eff = std::max(best_eff, seg_eff(n));
+        for (int n = 1; n <= max_n; ++n)
+            if (seg_eff(n) >= best_eff - 0.005) { best_n = n; break; } // among near-optimal splits the coarsest: fewer ramps
+        g.SEG = seg_of(best_n);
+        static const int seg_forced = std::getenv("FG_B200_TRI_SEG") ? std::atoi(std::getenv("FG_B200_TRI_SEG")) : 0; // experiments
+        if (seg_forced > 0) g.SEG = seg_forced;
+        g.n_segs = (band + g.SEG - 1) / g.SEG;
+        g.inv_delta = (float)(1.0 / delta);
+        pl.cfg = g;
+        pl.spw = spw;
+        pl.ok = true;
+        break;
+    }
+    return pl;
+}
+
 template <int SP, bool LG, bool ST>
 cudaError_t strip_attr(int smem) {
     return cudaFuncSetAttribute(k_pixelwise_strip<SP, LG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -214,6 +316,10 @@ int tile_setup(fg_ctx* ctx) {
     if ((e = cudaFuncSetAttribute(k_pixelwise_skew<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pixelwise_skew<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_skew)");
+    if ((e = cudaFuncSetAttribute(k_pixelwise_tri<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_tri<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_tri<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+        return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_tri)");
     return FG_OK;
 }
 
@@ -260,7 +366,7 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     const size_t bm_plane_words = (size_t)g.bm_rows * g.bm_pitchw;
     if (bm_plane_words * (size_t)n_planes * 4 > ((size_t)12 << 30) || g.bm_pitchw * 32u / 256u + 1u > 65535u) return 1;
     const size_t n_rows_all = (size_t)g.bm_rows * n_planes;
-    const size_t pg_bytes = n_rows_all * g.ppitch * 4;
+    const size_t pg_bytes = n_rows_all * g.ppitch * 4 + 256; // + slack: bulk copies of the last row read up to 3 entries past its window
     if (staged && (pg_bytes > ctx->table_max / 2 || g.bm_rows > 2000000)) return 2;
     int rc;
     if ((rc = ensure(ctx, ctx->thr, n_in * 16))) return rc;
@@ -356,9 +462,25 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     const float2* off = (const float2*)d_offsets;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
     SkewPlan sk{};
-    if (staged && skew_ok) sk = skew_plan(ctx, p, c, n_planes, table_dens);
+    TriPlan tr{};
+    if (staged && skew_ok) tr = tri_plan(ctx, p, c, n_planes, table_dens);
+    if (staged && skew_ok && !tr.ok) sk = skew_plan(ctx, p, c, n_planes, table_dens);
     uint32_t units_run = units;
-    if (sk.ok) {
+    if (tr.ok) {
+        TriCfg& k = tr.cfg;
+        k.bm_i0 = g.bm_i0; k.bm_j0 = g.bm_j0; k.bm_cols = g.bm_cols; k.bm_rows = g.bm_rows; k.ppitch = g.ppitch; k.r2c = g.r2c;
+        units_run = (uint32_t)k.n_strips * k.n_segs * n_planes;
+        if (units_run > units) { // the list was sized for the strip kernel's segments
+            if ((rc = ensure(ctx, ctx->tiles, (size_t)units_run * sizeof(TileRef) + 64))) return rc;
+            d_fbcount = (uint32_t*)ctx->tiles.p;
+            d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
+            FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+        }
+        if (tr.spw == 2) k_pixelwise_tri<2><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
+        else if (tr.spw == 4) k_pixelwise_tri<4><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
+        else k_pixelwise_tri<8><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
+        g.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
+    } else if (sk.ok) {
         SkewCfg& k = sk.cfg;
         k.bm_i0 = g.bm_i0; k.bm_j0 = g.bm_j0; k.bm_cols = g.bm_cols; k.bm_rows = g.bm_rows; k.ppitch = g.ppitch; k.r2c = g.r2c;
         units_run = (uint32_t)k.n_strips * k.n_segs * n_planes;
@@ -398,7 +520,10 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
                      (int)staged, g.TH, g.SEG, g.RH, g.CWB, g.GCAP, g.total, units);
     ctx->stats.tiles_total += units_run;
     ctx->strip_launches += 1;
-    ctx->eval_kernel = sk.ok ? "k_pixelwise_skew" : "k_pixelwise_strip";
+    ctx->eval_kernel = tr.ok ? "k_pixelwise_tri" : (sk.ok ? "k_pixelwise_skew" : "k_pixelwise_strip");
+    if (std::getenv("FG_B200_DEBUG") && tr.ok)
+        std::fprintf(stderr, "[fg] tri m=%d D=%d AMAX=%d NQ=%d PS=%d MCAP=%d GS=%d RH=%d NB=%d SEG=%d segs=%d smem=%u dens=%.3f\n", tr.cfg.m, tr.cfg.D, tr.cfg.AMAX,
+                     tr.cfg.NQ, tr.cfg.PS, tr.cfg.MCAP, tr.cfg.GS, tr.cfg.RH, tr.cfg.NB, tr.cfg.SEG, tr.cfg.n_segs, tr.cfg.total, table_dens);
     if (std::getenv("FG_B200_DEBUG") && sk.ok)
         std::fprintf(stderr, "[fg] skew D=%d PS=%d MCAP=%d TCAP=%d R=%d SEG=%d segs=%d smem=%u dens=%.3f\n", sk.cfg.D, sk.cfg.PS, sk.cfg.MCAP, sk.cfg.TCAP, sk.cfg.R,
                      sk.cfg.SEG, sk.cfg.n_segs, sk.cfg.total, table_dens);
