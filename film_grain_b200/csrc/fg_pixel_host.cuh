@@ -205,8 +205,10 @@ struct TriPlan { TriCfg cfg; int spw; bool ok; };
 TriPlan tri_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_planes, double dens) {
     TriPlan pl{};
     pl.ok = false;
-    static const bool enabled = std::getenv("FG_B200_TRI") && std::atoi(std::getenv("FG_B200_TRI")) != 0; // work in progress: slower than k_pixelwise_strip at C2
-    if (!enabled || c.rad.lognorm || p->rm != p->delta || p->n_samples > 8u * FG_TRI_WARPS || p->n_samples == 0) return pl;
+    static const bool enabled = !(std::getenv("FG_B200_TRI") && std::atoi(std::getenv("FG_B200_TRI")) == 0);
+    // Measured on a B200: 33 ms against 36 ms for k_pixelwise_strip at C2 (N = 256), but 144 ms against 86 ms at C4 (N = 64:
+    // four samples per evaluation warp do not cover the loader's per-step latency chain) -- the kernel is used for N > 128.
+    if (!enabled || c.rad.lognorm || p->rm != p->delta || p->n_samples > (uint32_t)FG_TRI_SPW_C * FG_TRI_WARPS || p->n_samples <= (uint32_t)FG_TRI_SPW_B * FG_TRI_WARPS) return pl;
     const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
     const double ox = (double)c.off_max_x - (double)c.off_min_x;
     const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0 + 3.0; // + alignment shift
@@ -215,17 +217,22 @@ TriPlan tri_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, i
     const int PS = (CWB + 1 + 7) / 8 * 8;
     const double cpr = inv_zoom / delta; // cell rows per output pixel row
     if (!(cpr > 0.05 && cpr < 24.0)) return pl;
-    const int spw = p->n_samples <= 2u * FG_TRI_WARPS ? 2 : (p->n_samples <= 4u * FG_TRI_WARPS ? 4 : 8);
+    const int spw = FG_TRI_SPW_C;
     const int band = c.row_end - c.row_begin;
     const int skrange = (int)std::nearbyint((double)c.off_max_y * (double)p->zoom) - (int)std::nearbyint((double)c.off_min_y * (double)p->zoom);
     if (skrange < 0 || skrange > 200) return pl;
     const size_t smem_max = ctx->smem_optin;
     static const int m_forced = std::getenv("FG_B200_TRI_M") ? std::atoi(std::getenv("FG_B200_TRI_M")) : 0; // experiments
+    // Step height m: the ring of merged rows and the staging buffer share what shared memory is left, in proportion to their
+    // expected sizes.  `headroom` = capacity / expectation; local density fluctuates a lot (a window only sees a few
+    // input pixels of a zoomed image, and -ln(1 - u) is heavy-tailed), so the largest m with a headroom of 2.5 is taken,
+    // else the m with the most headroom; below 1.6 the strip kernel is the better choice.
     static const int m_candidates[] = {16, 12, 8, 6, 4, 3, 2, 1};
+    double best_h = 0.0;
+    TriCfg best{};
     for (int m : m_candidates) {
         if (m_forced > 0 && m != m_forced) continue;
         if (m * spw > 32) continue;
-        if (m > 1 && m * cpr < 1.0 - 1e-9) { /* fine: larger steps */ }
         const int A = (int)std::ceil(m * cpr - 1e-9);
         if (A < 1 && m < 16) continue; // at least one cell row per step
         TriCfg g{};
@@ -238,35 +245,46 @@ TriPlan tri_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, i
         g.CWB = CWB;
         g.PS = PS;
         int RH = 4;
-        while (RH < 2 * m + skrange + 2) RH <<= 1;
+        while (RH < 3 * m + skrange + 2) RH <<= 1; // the evaluation warps may be a step ahead of the rows being finalised
         g.RH = RH;
         g.NB = std::max(1, 32 / (m * spw));
-        const double row_grains = (double)CWB * dens; // of one source row's window
-        g.GS = (int)align_up((uint32_t)(g.NG * (row_grains * 1.7 + 16.0) * 10.0) + 512u, 128);
         uint32_t off = 0;
         g.off_zq = off; off = align_up(off + (uint32_t)PS * 2u, 128);
         g.off_zp = off; off = align_up(off + (uint32_t)PS * 4u, 128);
         g.off_praw = off; off = align_up(off + (uint32_t)g.NG * PS * 4u, 128);
-        g.off_gs = off; off = align_up(off + (uint32_t)g.GS, 128);
         g.off_sinfo = off; off = align_up(off + (uint32_t)g.NG * 32u, 128);
         g.off_ext = off; off = align_up(off + 2u * (uint32_t)g.NG * 16u, 128);
         g.off_minfo = off; off = align_up(off + (uint32_t)g.NQ * 4u, 128);
-        g.off_state = off; off = align_up(off + 64u, 128);
+        g.off_state = off; off = align_up(off + 256u, 128);
         g.off_items = off; off = align_up(off + (uint32_t)FG_TRI_WARPS * 512u, 128);
-        g.off_hb = off; off = align_up(off + (uint32_t)(RH + 1) * 32u * spw * 4u, 128);
+        g.off_hb = off; off = align_up(off + (uint32_t)(RH + 1) * align_up((uint32_t)FG_TRI_WARPS * spw * 4u, 128), 128);
         g.off_Q = off; off = align_up(off + (uint32_t)g.NQ * PS * 2u, 128);
-        if ((size_t)off + 8u * 1024u > smem_max) continue;
-        uint32_t mcap = (uint32_t)((smem_max - off) / 8u);
-        mcap = std::min<uint32_t>(mcap, 65000u);
+        if ((size_t)off + 16u * 1024u > smem_max) continue;
+        const double row_grains = (double)CWB * dens + 1.0; // of one source row's window
         // live rows: the window, the rows being merged, and the row a wrap leaves unused at the end of the ring
-        const double need = 3.0 * row_grains * (double)(g.NQ + 1);
+        const double need_m = 3.0 * row_grains * (double)(g.NQ + 1) * 8.0;
+        const double need_gs = (double)g.NG * (row_grains + 16.0) * 10.0;
+        const double left = (double)(smem_max - off) - 1024.0;
+        double h = left / (need_m + need_gs);
+        uint32_t gs = align_up((uint32_t)std::min(h * need_gs, 100.0e3) + 256u, 128);
+        uint32_t mcap = (uint32_t)std::min<double>(((double)(smem_max - off) - (double)gs) / 8.0, 65000.0);
+        h = std::min(h, (double)mcap * 8.0 / need_m);
         if (std::getenv("FG_B200_DEBUG"))
-            std::fprintf(stderr, "[fg] tri_plan m=%d spw=%d A=%d NQ=%d PS=%d GS=%d RH=%d fixed=%u mcap=%u need=%.0f dens=%.3f\n", m, spw, A, g.NQ, PS, g.GS, RH, off, mcap, need, dens);
-        if ((double)mcap < 1.3 * need + 128.0) continue;
+            std::fprintf(stderr, "[fg] tri_plan m=%d spw=%d A=%d NQ=%d PS=%d GS=%u RH=%d fixed=%u mcap=%u headroom=%.2f dens=%.3f\n", m, spw, A, g.NQ, PS, gs, RH, off, mcap, h, dens);
+        g.GS = (int)gs;
+        g.off_gs = off; off += gs;
         g.MCAP = (int)mcap;
         g.off_M = off; off += mcap * 8u;
         g.total = off;
         if (off > smem_max) continue;
+        if (h > best_h) { best_h = h; best = g; }
+        if (h >= 2.5) break;
+    }
+    const char* mh = std::getenv("FG_B200_TRI_MIN_HEADROOM"); // tests: force the kernel onto dense content (skipped groups)
+    if (best_h < (mh ? std::atof(mh) : 1.6)) return pl;
+    {
+        TriCfg g = best;
+        const int m = g.m;
         // segment height: wave efficiency x (1 - ramp share)
         g.n_strips = (int)((p->out_w + 31) / 32);
         const long long per_seg_units = (long long)g.n_strips * n_planes;
@@ -292,7 +310,6 @@ TriPlan tri_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, i
         pl.cfg = g;
         pl.spw = spw;
         pl.ok = true;
-        break;
     }
     return pl;
 }
@@ -316,9 +333,7 @@ int tile_setup(fg_ctx* ctx) {
     if ((e = cudaFuncSetAttribute(k_pixelwise_skew<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pixelwise_skew<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_skew)");
-    if ((e = cudaFuncSetAttribute(k_pixelwise_tri<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_tri<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
-        (e = cudaFuncSetAttribute(k_pixelwise_tri<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_pixelwise_tri<FG_TRI_SPW_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_tri)");
     return FG_OK;
 }
@@ -457,7 +472,11 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         tab.Gg = d_G;
         tab.R2g = d_R2;
         tab.Cg = d_C;
-        table_dens = (double)total / ((double)n_rows_all * (double)g.bm_cols);
+        {   // grains per cell EXPECTED in the band: the average row capacity is expectation + slack_sigma * sqrt(expectation) + 64
+            const double cap_row = (double)total / (double)n_rows_all, k = ctx->table_slack_sigma;
+            const double rt = (-k + std::sqrt(k * k + 4.0 * std::max(cap_row - 64.0, 0.0))) * 0.5;
+            table_dens = rt * rt / (double)g.bm_cols;
+        }
     }
     const float2* off = (const float2*)d_offsets;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
@@ -476,9 +495,7 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
             d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
             FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
         }
-        if (tr.spw == 2) k_pixelwise_tri<2><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
-        else if (tr.spw == 4) k_pixelwise_tri<4><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
-        else k_pixelwise_tri<8><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
+        k_pixelwise_tri<FG_TRI_SPW_C><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
         g.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
     } else if (sk.ok) {
         SkewCfg& k = sk.cfg;

@@ -115,6 +115,44 @@ def test_pixelwise_matches_oracle(ctx, name, w, h, kw, path):
     assert 0.0 < ref.mean() < 1.0
 
 
+TRI_CASES = [
+    # k_pixelwise_tri (fg_tri.cuh): rm == delta, constant radius, 128 < N <= 256
+    ("tri_N256_noise", 100, 90, dict(radius=0.1, n_samples=256), "noise"),
+    ("tri_N200_partial_warps", 70, 50, dict(radius=0.1, n_samples=200), "noise"),
+    ("tri_N129", 40, 37, dict(radius=0.1, n_samples=129), "gradient"),
+    ("tri_r0.05_zoom2", 40, 30, dict(radius=0.05, n_samples=160, zoom=2.0), "noise"),
+    ("tri_r0.25_zoom0.7_sigma1.6", 90, 70, dict(radius=0.25, n_samples=144, zoom=0.7, sigma_px=1.6), "noise"),
+    ("tri_r0.5", 64, 64, dict(radius=0.5, n_samples=192), "gradient"),
+    ("tri_size_not_multiple_of_32", 45, 33, dict(radius=0.1, n_samples=256, zoom=1.3, size=(59, 43)), "noise"),
+    # dense content: groups of cell rows that do not fit the merged ring are skipped and their samples walk the cell table
+    ("tri_dense_gradient", 96, 64, dict(radius=0.1, n_samples=256), "gradient"),
+    ("tri_saturated_block", 96, 80, dict(radius=0.1, n_samples=160), "saturated"),
+]
+
+
+@pytest.mark.parametrize("name,w,h,kw,content", TRI_CASES, ids=[c[0] for c in TRI_CASES])
+def test_tri_kernel_matches_oracle(ctx, monkeypatch, name, w, h, kw, content):
+    """The merged-triple evaluation kernel against the oracle: full render and a row band, bit for bit; the test also
+    pins that the kernel under test really ran (fg_last_eval_kernel).  The planner leaves dense content to the strip
+    kernel; here it is told not to, so that the skipped-group path (samples walking the cell table) is exercised."""
+    monkeypatch.setenv("FG_B200_TRI_MIN_HEADROOM", "0.05")
+    p = O.make_params(algo=O.ALGO_PIXEL, **kw)
+    d, off, off_in = O.derive_common(p, w, h)
+    img = gradient_u8(w, h) if content == "gradient" else noise_u8(w, h, seed=23)
+    if content == "saturated":
+        img[20:60, 30:, :] = 255
+    lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
+    ref = O.render_pixelwise(lam, p, d, off_in)
+    got = ctx.render_pixelwise(fg_params_from(p, d, path=3), lam, off_in)
+    assert ctx.eval_kernel_name() == "k_pixelwise_tri"
+    diff = np.abs(ref - got)
+    assert diff.max() == 0.0, f"max diff {diff.max()} at {np.unravel_index(diff.argmax(), diff.shape)}; {np.count_nonzero(diff)} px differ"
+    oh = ref.shape[0]
+    r0, r1 = oh // 3, oh // 3 + max(1, oh // 4)
+    band = ctx.render_pixelwise(fg_params_from(p, d, path=3, rows=(r0, r1)), lam, off_in)
+    assert np.array_equal(band[r0:r1], ref[r0:r1])
+
+
 @pytest.mark.parametrize("path", [2, 3], ids=["tiled", "staged"])
 def test_tiled_path_is_taken_and_fallback_is_exact(ctx, path):
     """The strip kernel serves ordinary content itself; saturated content (u8 255 -> 4.4 grains per
