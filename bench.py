@@ -618,19 +618,18 @@ def main():
             image_check = check_against_oracle(prep, sm, device_image0)
         if wl["algo"] == "pixel":
             ao = algorithmic_ops(wl, d.block, d.offsets_input, n_cell, n_test)
-            # dominant kernel: the evaluation kernel (k_pixelwise_skew / k_pixelwise_strip).  Its algorithmic work is the
+            # dominant kernel: the evaluation kernel (k_pixelwise_tri / k_pixelwise_strip).  Its algorithmic work is the
             # evaluation term of SURVEY 8(d); the generation term belongs to the bitmap + cell-table kernels that
             # run before it and is reported beside it ("table") and in the whole-step figure ("pipeline").
             kernel_ms = (strip_total_ms / args.steps) if strip_total_ms > 0 else ms_per_step
             tab_ms = table_total_ms / args.steps
             achieved = ao["ops_eval"] / strip_launches / (kernel_ms * 1e-3) / 1e12
             traffic, issue_active, prof_src = None, None, None
-            prof = os.path.join(ROOT, "profiles", "strip_dram_bytes.json")
+            prof = os.path.join(ROOT, "profiles", "eval_kernel_static.json")
             if os.path.exists(prof):
                 try:
-                    pj = json.load(open(prof))
-                    traffic, issue_active = pj.get(args.workload), pj.get(args.workload + "_issue_active")
-                    prof_src = pj.get("source")
+                    pj = json.load(open(prof)).get(args.workload, {}).get(ctx.eval_kernel_name(), {})
+                    traffic, issue_active, prof_src = pj.get("traffic"), pj.get("issue_active"), pj.get("source")
                 except Exception:
                     traffic = None
             io_bytes = planes * (wl["w"] * wl["h"] * 16 + out_w * out_h * 4)  # thr+e planes in, f32 plane out

@@ -626,9 +626,11 @@ k_pixelwise_tri(const float* __restrict__ lambda, size_t in_stride, const float2
                         }
                     }
                     // grains: warps over the source rows, lanes over a row's grains (two per lane and trip: their loads overlap).
-                    // A grain with window-local index g in window column e goes to
-                    //   triple r     at  start(r)   - f(r+1) - f(r+2) + P[r+1][e]   + P[r+2][e]   + g   (its row is the triple's first),
-                    //   triple r - 1 at  start(r-1) - f(r-1) - f(r+1) + P[r-1][e+1] + P[r+1][e]   + g   (second),
+                    // Inside a column of triple d the grains of its CENTRE row d + 1 come first (a sample's own cell row: the
+                    // candidates most likely to cover it are tested first), then row d, then row d + 2.  A grain with window-local
+                    // index g in window column e therefore goes to
+                    //   triple r     at  start(r)   - f(r+1) - f(r+2) + P[r+1][e+1] + P[r+2][e]   + g   (its row is the triple's first),
+                    //   triple r - 1 at  start(r-1) - f(r-1) - f(r+1) + P[r-1][e]   + P[r+1][e]   + g   (centre),
                     //   triple r - 2 at  start(r-2) - f(r-2) - f(r-1) + P[r-2][e+1] + P[r-1][e+1] + g   (third).
                     for (int r = dw; r < NGu; r += ND) {
                         const uint32_t sa = SINFO + (uint32_t)r * 32u;
@@ -642,15 +644,17 @@ k_pixelwise_tri(const float* __restrict__ lambda, size_t in_stride, const float2
                             const uint32_t c0 = tri_lds_u16(ri.w + g0 * 2u), c1 = v1 ? tri_lds_u16(ri.w + g1 * 2u) : c0;
                             const float2 gr0 = lds_f32x2(ri.z + g0 * 8u), gr1 = lds_f32x2(ri.z + (v1 ? g1 : g0) * 8u);
                             const uint32_t e0 = ((c0 - tcolA_u) & 0xFFFFu) * 4u, e1 = ((c1 - tcolA_u) & 0xFFFFu) * 4u; // byte offsets of the grains' window columns
-                            const uint32_t x10 = tri_lds_u32(pp1 + e0), x20 = tri_lds_u32(pp2 + e0), y10 = tri_lds_u32(pm1 + e0 + 4u), y20 = tri_lds_u32(pm2 + e0 + 4u);
-                            const uint32_t x11 = tri_lds_u32(pp1 + e1), x21 = tri_lds_u32(pp2 + e1), y11 = tri_lds_u32(pm1 + e1 + 4u), y21 = tri_lds_u32(pm2 + e1 + 4u);
-                            if (t0) tri_sts_f32x2(Ms + (bi.x + g0 + x10 + x20) * 8u, gr0.y, gr0.x);
-                            if (t1) tri_sts_f32x2(Ms + (bi.y + g0 + y10 + x10) * 8u, gr0.y, gr0.x);
-                            if (t2) tri_sts_f32x2(Ms + (bi.z + g0 + y20 + y10) * 8u, gr0.y, gr0.x);
+                            const uint32_t a10 = tri_lds_u32(pp1 + e0), b10 = tri_lds_u32(pp1 + e0 + 4u), a20 = tri_lds_u32(pp2 + e0);
+                            const uint32_t m10 = tri_lds_u32(pm1 + e0), n10 = tri_lds_u32(pm1 + e0 + 4u), n20 = tri_lds_u32(pm2 + e0 + 4u);
+                            const uint32_t a11 = tri_lds_u32(pp1 + e1), b11 = tri_lds_u32(pp1 + e1 + 4u), a21 = tri_lds_u32(pp2 + e1);
+                            const uint32_t m11 = tri_lds_u32(pm1 + e1), n11 = tri_lds_u32(pm1 + e1 + 4u), n21 = tri_lds_u32(pm2 + e1 + 4u);
+                            if (t0) tri_sts_f32x2(Ms + (bi.x + g0 + b10 + a20) * 8u, gr0.y, gr0.x);
+                            if (t1) tri_sts_f32x2(Ms + (bi.y + g0 + m10 + a10) * 8u, gr0.y, gr0.x);
+                            if (t2) tri_sts_f32x2(Ms + (bi.z + g0 + n20 + n10) * 8u, gr0.y, gr0.x);
                             if (v1) {
-                                if (t0) tri_sts_f32x2(Ms + (bi.x + g1 + x11 + x21) * 8u, gr1.y, gr1.x);
-                                if (t1) tri_sts_f32x2(Ms + (bi.y + g1 + y11 + x11) * 8u, gr1.y, gr1.x);
-                                if (t2) tri_sts_f32x2(Ms + (bi.z + g1 + y21 + y11) * 8u, gr1.y, gr1.x);
+                                if (t0) tri_sts_f32x2(Ms + (bi.x + g1 + b11 + a21) * 8u, gr1.y, gr1.x);
+                                if (t1) tri_sts_f32x2(Ms + (bi.y + g1 + m11 + a11) * 8u, gr1.y, gr1.x);
+                                if (t2) tri_sts_f32x2(Ms + (bi.z + g1 + n21 + n11) * 8u, gr1.y, gr1.x);
                             }
                         }
                     }
