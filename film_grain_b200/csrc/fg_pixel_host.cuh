@@ -454,13 +454,16 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         float* d_R2 = (float*)((unsigned char*)ctx->gtab.p + g_bytes);
         uint16_t* d_C = (uint16_t*)((unsigned char*)ctx->gtab.p + g_bytes + r2_bytes);
         StageGeo geo{g.bm_i0, g.bm_j0, g.bm_cols, g.bm_rows, g.bm_pitchw, g.ppitch};
-        const unsigned ggrid = (unsigned)((n_rows_all + FG_GW_WARPS - 1) / FG_GW_WARPS);
-        if (c.rad.lognorm)
-            k_gen_rows<true><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
-                                                               d_rowbase, d_rowcap, d_G, d_R2, d_C, d_overflow, geo, n_planes, c);
-        else
-            k_gen_rows<false><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p,
-                                                                d_rowbase, d_rowcap, d_G, d_R2, d_C, d_overflow, geo, n_planes, c);
+        // three planes: one warp generates a cell row for all of them (one seeding and one Knuth chain per cell)
+        const bool joint = n_planes == 3 && !(std::getenv("FG_B200_GEN_JOINT") && std::atoi(std::getenv("FG_B200_GEN_JOINT")) == 0);
+        const size_t gwarps = joint ? (size_t)g.bm_rows : n_rows_all;
+        const unsigned ggrid = (unsigned)((gwarps + FG_GW_WARPS - 1) / FG_GW_WARPS);
+#define FG_LAUNCH_GEN(LG, NPL)                                                                                                   \
+    k_gen_rows<LG, NPL><<<ggrid, FG_GW_WARPS * 32, 0, s>>>(d_bm, bm_plane_words, d_e, d_lambda, in_stride, (uint32_t*)ctx->ptab.p, \
+                                                           d_rowbase, d_rowcap, d_G, d_R2, d_C, d_overflow, geo, n_planes, c)
+        if (c.rad.lognorm) { if (joint) FG_LAUNCH_GEN(true, 3); else FG_LAUNCH_GEN(true, 1); }
+        else { if (joint) FG_LAUNCH_GEN(false, 3); else FG_LAUNCH_GEN(false, 1); }
+#undef FG_LAUNCH_GEN
         FG_CUDA(ctx, cudaGetLastError());
         uint32_t overflow = 0;
         FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));

@@ -111,9 +111,24 @@ __device__ __forceinline__ uint64_t next_u64(Xoshiro& r) {
     return result;
 }
 __device__ __forceinline__ uint32_t next_u32(Xoshiro& r) { return (uint32_t)(next_u64(r) >> 32); }
+// the state update alone (skipping a draw whose value is not needed)
+__device__ __forceinline__ void advance(Xoshiro& r) {
+    const uint64_t t = r.s1 << 17;
+    r.s2 ^= r.s0;
+    r.s3 ^= r.s1;
+    r.s1 ^= r.s2;
+    r.s0 ^= r.s3;
+    r.s2 ^= t;
+    r.s3 = rotl64(r.s3, 45);
+}
+// a generator that counts its draws: k_gen_rows keeps one seed state per cell for all colour planes and
+// re-derives a plane's state after its Poisson draw by skipping that many outputs
+struct XoshiroCounted : Xoshiro { uint32_t n; };
+__device__ __forceinline__ uint64_t next_u64(XoshiroCounted& r) { ++r.n; return next_u64(static_cast<Xoshiro&>(r)); }
 
 // rand Standard: f64 in [0,1) with 53 bits
-__device__ __forceinline__ double standard_f64(Xoshiro& r) {
+template <class R>
+__device__ __forceinline__ double standard_f64(R& r) {
     return __dmul_rn((double)(next_u64(r) >> 11), 1.0 / 9007199254740992.0);
 }
 // rand Open01 f64
@@ -152,7 +167,8 @@ __device__ __forceinline__ uint32_t sat_u32(double v) {
 }
 
 // rand_distr 0.4.3 Poisson<f64>::new(lambda).sample(rng) as u32; lambda > 0.
-__device__ inline uint32_t poisson_f64(Xoshiro& r, double lambda) {
+template <class R>
+__device__ inline uint32_t poisson_f64(R& r, double lambda) {
     // Poisson::new rejects lambda <= 0 / NaN (the reference unwrap()s, i.e. panics); absurd means
     // would never terminate in reasonable time either.  Draw nothing instead of hanging the GPU.
     if (!(lambda > 0.0) || !(lambda < 1.0e15)) return 0u;

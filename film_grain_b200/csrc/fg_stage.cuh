@@ -100,51 +100,74 @@ struct StageGeo {
     uint32_t ppitch;          // Pg entries per row (>= cols + 1, multiple of 8)
 };
 
-// One WARP per (cell row, plane), no CTA-wide barriers.  The row is walked in tiles of FG_GW_TILE cells:
-// the tile's non-empty cells (first-draw bitmap) are compacted into a list and processed 32 at a time,
-// one lane per cell at full occupancy: seeding, second Knuth draw (76% of the non-empty cells at
-// lambda' = 1/pi stop there with one grain, whose position is drawn and stored at once), Knuth
-// continuation or the general Poisson sampler for the rest.  Cells with two or more grains are the
-// divergent tail: their generator state and destination are parked in a per-warp queue and their
-// positions are drawn 32 cells at a time when the queue fills.  A final scan over the tile's counts
-// writes the prefix entries of ALL its cells.
+// One WARP per cell row, no CTA-wide barriers.  NPL = 3: the warp generates the row for all three colour planes
+// together; NPL = 1: one warp per (plane, row), any plane count.  A cell is seeded from (seed, i, j) only
+// (src/rng.rs:26-29), and its Knuth chain p_k = U1 ... Uk is the same sequence for every plane -- a plane only decides
+// where it stops (p_k <= exp(-lambda'_plane), src/pixelwise.rs:76-85 via rand_distr's Poisson) -- so the hash, the
+// eight PCG seed words and the chain are computed ONCE per cell that is non-empty in any plane, and planes that stop at
+// the same count share their grain positions (the generator state after the Poisson draw is the same).
+//
+// The row is walked in tiles of FG_GW_TILE cells: the tile's non-empty cells (union of the planes' first-draw bitmaps)
+// are compacted into a list and processed 32 at a time, one lane per cell at full occupancy: seeding, two Knuth draws
+// (76% of the non-empty (cell, plane) pairs at lambda' = 1/pi stop there with one grain, whose position is drawn once
+// and stored for every such plane), Knuth continuation for the rest.  (Cell, plane) pairs with two or more grains are
+// the divergent tail: the generator state after the second draw, the number of outputs to skip and the destination are
+// parked in a per-warp queue and their positions are drawn 32 pairs at a time when the queue fills.  A lane one of whose
+// planes needs the general sampler (lambda' >= 12, e < 0) parks all its planes from the seed state instead, with the
+// sampler's own draw count as the skip.  A final scan over the tile's counts writes the prefix entries of ALL its cells.
 #define FG_GW_WARPS 4
-#define FG_GW_TILE 1024
+#ifndef FG_GW_TILE
+#define FG_GW_TILE 1024 // cells per tile: a multiple of 256 (phase c: FG_GW_TILE / 32 cells per lane, 8 per store pair)
+#endif
+#ifndef FG_GW_MINB
+#define FG_GW_MINB 1
+#endif
 #define FG_GW_QCAP 64
+template <int NPL>
 struct GenWarpSmem {
     uint16_t list[FG_GW_TILE];
-    __align__(16) uint16_t cnt[FG_GW_TILE];
+    __align__(16) uint16_t cnt[NPL][FG_GW_TILE];
     uint64_t q_s0[FG_GW_QCAP], q_s1[FG_GW_QCAP], q_s2[FG_GW_QCAP], q_s3[FG_GW_QCAP], q_dst[FG_GW_QCAP];
-    uint32_t q_q[FG_GW_QCAP];
+    uint32_t q_q[FG_GW_QCAP], q_skip[FG_GW_QCAP];
     float q_sx[FG_GW_QCAP];
     uint16_t q_col[FG_GW_QCAP];
 };
 
-template <bool LOGN>
-__global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
+template <bool LOGN, int NPL>
+__global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                                                                 const double* __restrict__ e_planes, const float* __restrict__ lambda,
                                                                 size_t in_stride, uint32_t* __restrict__ Pg,
                                                                 const uint64_t* __restrict__ rowbase, const uint32_t* __restrict__ rowcap,
                                                                 float2* __restrict__ Gg, float* __restrict__ R2g, uint16_t* __restrict__ Cg,
                                                                 uint32_t* __restrict__ overflow, StageGeo geo, int n_planes, RenderConsts c) {
-    __shared__ GenWarpSmem sm_all[FG_GW_WARPS];
+    __shared__ GenWarpSmem<NPL> sm_all[FG_GW_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    GenWarpSmem& sm = sm_all[warp];
-    const size_t ridx = (size_t)blockIdx.x * FG_GW_WARPS + warp;
-    if (ridx >= (size_t)geo.rows * n_planes) return; // whole warp
-    const int plane = (int)(ridx / geo.rows), row = (int)(ridx - (size_t)plane * geo.rows);
+    GenWarpSmem<NPL>& sm = sm_all[warp];
+    const size_t widx0 = (size_t)blockIdx.x * FG_GW_WARPS + warp;
+    if (widx0 >= (size_t)geo.rows * (NPL == 1 ? n_planes : 1)) return; // whole warp
+    const int plane0 = NPL == 1 ? (int)(widx0 / geo.rows) : 0, row = (int)(widx0 - (size_t)plane0 * geo.rows);
     const int j = geo.j0 + row;
     const float sy = __fmul_rn(__int2float_rn(j), c.delta);
     const int iy = min(max(floor_i32(sy), 0), c.in_h - 1);
-    const double* erow = e_planes + in_stride * plane + (size_t)iy * c.in_w;
-    const float* lrow = lambda + in_stride * plane + (size_t)iy * c.in_w;
-    const uint32_t* bmrow = bm_planes + bm_plane_words * plane + (size_t)row * geo.pitchw;
-    const uint64_t base = rowbase[ridx];
-    const uint32_t cap = rowcap[ridx];
-    uint32_t* prow = Pg + ridx * geo.ppitch;
+    const double* erow[NPL];
+    const float* lrow[NPL];
+    const uint32_t* bmrow[NPL];
+    uint64_t base[NPL];
+    uint32_t cap[NPL], run[NPL]; // run: grains of the row placed so far
+    uint32_t* prow[NPL];
+#pragma unroll
+    for (int pl = 0; pl < NPL; ++pl) {
+        const size_t ridx = (size_t)(plane0 + pl) * geo.rows + row;
+        erow[pl] = e_planes + in_stride * (plane0 + pl) + (size_t)iy * c.in_w;
+        lrow[pl] = lambda + in_stride * (plane0 + pl) + (size_t)iy * c.in_w;
+        bmrow[pl] = bm_planes + bm_plane_words * (plane0 + pl) + (size_t)row * geo.pitchw;
+        base[pl] = rowbase[ridx];
+        cap[pl] = rowcap[ridx];
+        prow[pl] = Pg + ridx * geo.ppitch;
+        run[pl] = 0;
+    }
     const uint32_t lt_mask = (1u << lane) - 1u;
-    uint32_t run = 0; // grains of the row placed so far
-    uint32_t qn = 0;  // parked cells
+    uint32_t qn = 0;  // parked (cell, plane) pairs
 
     auto warp_incl = [&](uint32_t v) {
 #pragma unroll
@@ -154,41 +177,76 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
         }
         return v;
     };
-    auto draw_grains = [&](Xoshiro& rng, float sx, uint64_t dst, uint32_t q, uint16_t col) {
-        for (uint32_t g = 0; g < q; ++g) {
-            const float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
-            const float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
-            Gg[dst + g] = make_float2(cx, cy);
-            Cg[dst + g] = col; // the grain's cell column in the table (mod 2^16): k_pixelwise_skew merges rows by column
-            if (LOGN) { // RadiusProfile::sample + clamp (src/model.rs:137-148, src/pixelwise.rs:89-95)
-                const float radius = radius_sample_clamped(c.rad, rng);
-                R2g[dst + g] = radius > 0.0f ? __fmul_rn(radius, radius) : -1.0f;
-            }
+    auto warp_incl64 = [&](uint64_t v) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t u = __shfl_up_sync(0xFFFFFFFFu, v, d);
+            if (lane >= d) v += u;
         }
+        return v;
     };
-    auto flush = [&]() {
+    // Draw the parked pairs, 32 at a time from the top of the queue and two grains per round: a pair with more than two
+    // grains left goes back into the queue with its advanced state, so every round runs at full lane occupancy whatever
+    // the counts are.  `all` = the row is finished: drain the partial rounds too.
+    auto flush = [&](bool all) {
         __syncwarp();
-        for (uint32_t b = 0; b < qn; b += 32) {
-            const uint32_t t = b + lane;
+        while (qn >= 32u || (all && qn)) {
+            const uint32_t b = qn >= 32u ? qn - 32u : 0u, t = b + lane;
+            bool again = false;
+            Xoshiro rng;
+            float sx = 0.0f;
+            uint64_t dst = 0;
+            uint32_t q = 0;
+            uint16_t col = 0;
             if (t < qn) {
-                Xoshiro rng;
                 rng.s0 = sm.q_s0[t]; rng.s1 = sm.q_s1[t]; rng.s2 = sm.q_s2[t]; rng.s3 = sm.q_s3[t];
-                draw_grains(rng, sm.q_sx[t], sm.q_dst[t], sm.q_q[t], sm.q_col[t]);
+                for (uint32_t k = sm.q_skip[t]; k; --k) advance(rng);
+                sx = sm.q_sx[t];
+                dst = sm.q_dst[t];
+                q = sm.q_q[t];
+                col = sm.q_col[t];
+                const uint32_t now = min(q, 2u);
+                for (uint32_t g = 0; g < now; ++g) {
+                    const float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
+                    const float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
+                    Gg[dst + g] = make_float2(cx, cy);
+                    Cg[dst + g] = col; // the grain's cell column in the table (mod 2^16): the evaluation kernels merge rows by column
+                    if (LOGN) { // RadiusProfile::sample + clamp (src/model.rs:137-148, src/pixelwise.rs:89-95)
+                        const float radius = radius_sample_clamped(c.rad, rng);
+                        R2g[dst + g] = radius > 0.0f ? __fmul_rn(radius, radius) : -1.0f;
+                    }
+                }
+                again = q > 2u;
             }
+            __syncwarp(); // every lane has read its entry before the survivors overwrite the slots
+            const uint32_t am = __ballot_sync(0xFFFFFFFFu, again);
+            if (again) {
+                const uint32_t slot = b + __popc(am & lt_mask);
+                sm.q_s0[slot] = rng.s0; sm.q_s1[slot] = rng.s1; sm.q_s2[slot] = rng.s2; sm.q_s3[slot] = rng.s3;
+                sm.q_dst[slot] = dst + 2u;
+                sm.q_q[slot] = q - 2u;
+                sm.q_skip[slot] = 0u;
+                sm.q_sx[slot] = sx;
+                sm.q_col[slot] = col;
+            }
+            qn = b + __popc(am);
+            __syncwarp();
         }
-        qn = 0;
-        __syncwarp();
     };
 
     for (int tile0 = 0; tile0 < (int)geo.ppitch; tile0 += FG_GW_TILE) {
         // ---- a: clear the counts, compact the tile's non-empty cells into `list` ----
         {
-            uint4* cz = (uint4*)sm.cnt; // 2 KiB = 128 x 16 B
+            uint4* cz = (uint4*)&sm.cnt[0][0]; // NPL x 2 KiB
 #pragma unroll
-            for (int k = 0; k < FG_GW_TILE * 2 / 16 / 32; ++k) cz[lane + 32 * k] = make_uint4(0, 0, 0, 0);
+            for (int k = 0; k < NPL * FG_GW_TILE * 2 / 16 / 32; ++k) cz[lane + 32 * k] = make_uint4(0, 0, 0, 0);
         }
         const uint32_t widx = (uint32_t)(tile0 >> 5) + (uint32_t)lane;
-        uint32_t bits = widx < geo.pitchw ? __ldg(bmrow + widx) : 0u;
+        uint32_t bits = 0u;
+        if (lane < FG_GW_TILE / 32 && widx < geo.pitchw) {
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) bits |= __ldg(bmrow[pl] + widx);
+        }
         const uint32_t nb = __popc(bits);
         const uint32_t inclA = warp_incl(nb);
         const uint32_t M = __shfl_sync(0xFFFFFFFFu, inclA, 31);
@@ -204,66 +262,162 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
         // ---- b: 32 non-empty cells at a time ----
         for (uint32_t b0 = 0; b0 < M; b0 += 32) {
             const uint32_t t = b0 + lane;
-            uint32_t q = 0, cl = 0;
-            Xoshiro rng;
+            uint32_t q[NPL], skip[NPL];
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) { q[pl] = 0; skip[pl] = 0; }
+            uint32_t cl = 0;
+            Xoshiro sb; // state the lane's planes are drawn from: after two outputs, or the seed state (general lanes)
+            sb.s0 = sb.s1 = sb.s2 = sb.s3 = 0;
+            bool genlane = false;
             float sx = 0.0f;
             if (t < M) {
                 cl = sm.list[t];
                 const int i = geo.i0 + tile0 + (int)cl;
                 sx = __fmul_rn(__int2float_rn(i), c.delta);
                 const int ix = min(max(floor_i32(sx), 0), c.in_w - 1);
-                const double e = __ldg(erow + ix);
+                double e[NPL];
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    e[pl] = __ldg(erow[pl] + ix);
+                    genlane |= e[pl] < 0.0;
+                }
+                Xoshiro rng;
                 seed_small_rng(rng, mix3_row(mix3_col(c.seed_cell, i), j), c.seeding);
-                if (e < 0.0) { // lambda' >= 12 or non-finite: the general sampler (src/pixelwise.rs:82-85)
-                    const float lam = __ldg(lrow + ix);
-                    q = poisson_f64(rng, (double)__fmul_rn(__fmul_rn(lam, c.delta), c.delta));
+                if (genlane) { // some plane has lambda' >= 12 or a non-finite mean: the general sampler (src/pixelwise.rs:82-85)
+                    sb = rng;
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl) {
+                        XoshiroCounted rc;
+                        rc.s0 = rng.s0; rc.s1 = rng.s1; rc.s2 = rng.s2; rc.s3 = rng.s3; rc.n = 0;
+                        if (e[pl] < 0.0) {
+                            const float lam = __ldg(lrow[pl] + ix);
+                            q[pl] = poisson_f64(rc, (double)__fmul_rn(__fmul_rn(lam, c.delta), c.delta));
+                        } else {
+                            double p = standard_f64(rc);
+                            while (p > e[pl]) { p = __dmul_rn(p, standard_f64(rc)); ++q[pl]; }
+                        }
+                        skip[pl] = rc.n;
+                    }
                 } else {
                     double p = standard_f64(rng);
-                    while (p > e) { p = __dmul_rn(p, standard_f64(rng)); ++q; }
+                    uint32_t act = 0;
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl) act |= (p > e[pl]) ? (1u << pl) : 0u;
+                    p = __dmul_rn(p, standard_f64(rng));
+                    sb = rng;
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl) {
+                        q[pl] = (act >> pl) & 1u;
+                        if (!(p > e[pl])) act &= ~(1u << pl);
+                    }
+                    while (act) {
+                        p = __dmul_rn(p, standard_f64(rng));
+#pragma unroll
+                        for (int pl = 0; pl < NPL; ++pl) {
+                            q[pl] += (act >> pl) & 1u;
+                            if (!(p > e[pl])) act &= ~(1u << pl);
+                        }
+                    }
+#pragma unroll
+                    for (int pl = 0; pl < NPL; ++pl) skip[pl] = q[pl] - 1u; // q >= 2 pairs only
                 }
             }
-            const uint32_t inclB = warp_incl(q);
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inclB, 31);
-            if ((uint64_t)run + total > cap || __any_sync(0xFFFFFFFFu, q > 65535u)) { // uniform
+            bool big = false;
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) big |= q[pl] > 65535u;
+            if (__any_sync(0xFFFFFFFFu, big)) { // uniform: a cell with more grains than the 16-bit counts hold
                 if (lane == 0) atomicExch(overflow, 1u);
                 return;
             }
-            const uint64_t dst = base + run + (inclB - q);
-            if (q) sm.cnt[cl] = (uint16_t)q;
-            const bool parked = q >= 2u;
-            const uint32_t pm = __ballot_sync(0xFFFFFFFFu, parked);
-            const uint16_t col16 = (uint16_t)((uint32_t)tile0 + cl);
-            if (q == 1u) draw_grains(rng, sx, dst, 1u, col16);
-            if (parked) {
-                const uint32_t slot = qn + __popc(pm & lt_mask);
-                sm.q_s0[slot] = rng.s0; sm.q_s1[slot] = rng.s1; sm.q_s2[slot] = rng.s2; sm.q_s3[slot] = rng.s3;
-                sm.q_dst[slot] = dst;
-                sm.q_q[slot] = q;
-                sm.q_sx[slot] = sx;
-                sm.q_col[slot] = col16;
+            uint32_t excl[NPL], total[NPL];
+            if (NPL == 3) { // three 21-bit fields: 32 x 65535 < 2^21
+                const uint64_t v = (uint64_t)q[0] | ((uint64_t)q[NPL > 1 ? 1 : 0] << 21) | ((uint64_t)q[NPL > 2 ? 2 : 0] << 42);
+                const uint64_t incl = warp_incl64(v);
+                const uint64_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31), ex = incl - v;
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    excl[pl] = (uint32_t)(ex >> (21 * pl)) & 0x1FFFFFu;
+                    total[pl] = (uint32_t)(tot >> (21 * pl)) & 0x1FFFFFu;
+                }
+            } else {
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl) {
+                    const uint32_t incl = warp_incl(q[pl]);
+                    total[pl] = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    excl[pl] = incl - q[pl];
+                }
             }
-            qn += __popc(pm);
-            if (qn > FG_GW_QCAP - 32) flush();
-            run += total;
+            bool over = false;
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) over |= (uint64_t)run[pl] + total[pl] > cap[pl];
+            if (over) { // uniform
+                if (lane == 0) atomicExch(overflow, 1u);
+                return;
+            }
+            uint64_t dst[NPL];
+            const uint16_t col16 = (uint16_t)((uint32_t)tile0 + cl);
+            uint32_t one = 0; // planes whose cell holds exactly one grain: its position is drawn once, here
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) {
+                dst[pl] = base[pl] + run[pl] + excl[pl];
+                if (q[pl]) sm.cnt[pl][cl] = (uint16_t)q[pl];
+                if (q[pl] == 1u && !genlane) one |= 1u << pl;
+                run[pl] += total[pl];
+            }
+            if (one) {
+                Xoshiro rng = sb;
+                const float cx = __fadd_rn(sx, uniform_f32(rng, c.uscale_cell));
+                const float cy = __fadd_rn(sy, uniform_f32(rng, c.uscale_cell));
+                float r2 = 0.0f;
+                if (LOGN) {
+                    const float radius = radius_sample_clamped(c.rad, rng);
+                    r2 = radius > 0.0f ? __fmul_rn(radius, radius) : -1.0f;
+                }
+#pragma unroll
+                for (int pl = 0; pl < NPL; ++pl)
+                    if ((one >> pl) & 1u) {
+                        Gg[dst[pl]] = make_float2(cx, cy);
+                        Cg[dst[pl]] = col16;
+                        if (LOGN) R2g[dst[pl]] = r2;
+                    }
+            }
+#pragma unroll
+            for (int pl = 0; pl < NPL; ++pl) {
+                const bool parked = q[pl] != 0u && !((one >> pl) & 1u);
+                const uint32_t pm = __ballot_sync(0xFFFFFFFFu, parked);
+                if (parked) {
+                    const uint32_t slot = qn + __popc(pm & lt_mask);
+                    sm.q_s0[slot] = sb.s0; sm.q_s1[slot] = sb.s1; sm.q_s2[slot] = sb.s2; sm.q_s3[slot] = sb.s3;
+                    sm.q_dst[slot] = dst[pl];
+                    sm.q_q[slot] = q[pl];
+                    sm.q_skip[slot] = skip[pl];
+                    sm.q_sx[slot] = sx;
+                    sm.q_col[slot] = col16;
+                }
+                qn += __popc(pm);
+                if (qn >= 32u) flush(false); // leaves fewer than 32 parked: the next plane adds at most 32
+            }
         }
         __syncwarp(); // cnt complete
-        // ---- c: prefix entries of the tile's cells: lane l owns cells 32 l .. 32 l + 31 ----
-        {
-            const uint4* cs = (const uint4*)(sm.cnt + 32 * lane);
-            uint4 v[4];
+        // ---- c: prefix entries of the tile's cells: lane l owns FG_GW_TILE / 32 consecutive cells ----
+#pragma unroll
+        for (int pl = 0; pl < NPL; ++pl) {
+            constexpr int CPLN = FG_GW_TILE / 32, NV = CPLN / 8; // cells per lane, 16-byte count vectors per lane
+            const uint4* cs = (const uint4*)(sm.cnt[pl] + CPLN * lane);
+            uint4 v[NV];
             uint32_t s32 = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < NV; ++k) {
                 v[k] = cs[k];
                 s32 += (v[k].x & 0xFFFFu) + (v[k].x >> 16) + (v[k].y & 0xFFFFu) + (v[k].y >> 16) + (v[k].z & 0xFFFFu) + (v[k].z >> 16) +
                        (v[k].w & 0xFFFFu) + (v[k].w >> 16);
             }
             const uint32_t inclC = warp_incl(s32);
             const uint32_t tile_total = __shfl_sync(0xFFFFFFFFu, inclC, 31);
-            uint32_t pacc = run - tile_total + inclC - s32; // grains of the row before this lane's first cell
-            const int k0 = tile0 + 32 * lane;
+            uint32_t pacc = run[pl] - tile_total + inclC - s32; // grains of the row before this lane's first cell
+            const int k0 = tile0 + CPLN * lane;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < NV; ++k) {
                 const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
                 uint4 o0, o1;
                 o0.x = pacc; pacc += w[0] & 0xFFFFu;
@@ -275,7 +429,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
                 o1.z = pacc; pacc += w[3] & 0xFFFFu;
                 o1.w = pacc; pacc += w[3] >> 16;
                 if (k0 + 8 * k < (int)geo.ppitch) { // ppitch is a multiple of 8
-                    uint4* dstp = (uint4*)(prow + k0 + 8 * k);
+                    uint4* dstp = (uint4*)(prow[pl] + k0 + 8 * k);
                     dstp[0] = o0;
                     dstp[1] = o1;
                 }
@@ -283,7 +437,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32) k_gen_rows(const uint32_t* _
         }
         __syncwarp(); // cnt / list are rewritten by the next tile
     }
-    flush();
+    flush(true);
 }
 
 } // namespace fg

@@ -87,32 +87,46 @@ __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __res
     const int i = i0 + col;
     const uint64_t hcol = mix3_col(c.seed_cell, i);
     const int ix = min(max(floor_i32(__fmul_rn(__int2float_rn(i), c.delta)), 0), c.in_w - 1);
+    // the thresholds of a column change with the input row only (every 1/delta cell rows, the same row for every thread)
+    uint64_t thc[NP ? NP : 1];
+    int iy_held = -1;
 #pragma unroll 4
     for (int rr = 0; rr < FG_BM_ROWS; ++rr) {
         const int row = row0 + rr;
         if (row >= rows) break; // uniform
         const int j = j0 + row;
         uint64_t m1 = 0;
-        size_t pix = 0;
+        const int iy = min(max(floor_i32(__fmul_rn(__int2float_rn(j), c.delta)), 0), c.in_h - 1);
+        const size_t pix = (size_t)iy * c.in_w + ix;
         if (valid) {
             const uint64_t h = mix3_row(hcol, j);
             uint64_t s0, s3;
             if (SEEDING == 0) { s0 = pcg_word_pair<0>(h); s3 = pcg_word_pair<3>(h); }
             else { Xoshiro t; seed_splitmix(t, h); s0 = t.s0; s3 = t.s3; }
             m1 = (rotl64(s0 + s3, 23) + s0) >> 11;
-            const int iy = min(max(floor_i32(__fmul_rn(__int2float_rn(j), c.delta)), 0), c.in_h - 1);
-            pix = (size_t)iy * c.in_w + ix;
         }
-        const int np = NP ? NP : n_planes;
+        if (NP) {
+            if (iy != iy_held) { // uniform
+                iy_held = iy;
 #pragma unroll
-        for (int pl = 0; pl < np; ++pl) {
-            bool ne = false;
-            if (valid) {
-                const uint64_t th64 = __ldg(thr_planes + in_stride * pl + pix);
-                ne = (th64 == FG_THR_GENERAL) || (m1 > th64);
+                for (int pl = 0; pl < (NP ? NP : 1); ++pl) thc[pl] = valid ? __ldg(thr_planes + in_stride * pl + pix) : FG_THR_EMPTY;
             }
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne);
-            if (store) bm[bm_plane_words * pl + (size_t)row * pitchw + (col >> 5)] = m;
+#pragma unroll
+            for (int pl = 0; pl < (NP ? NP : 1); ++pl) {
+                const bool ne = valid && ((thc[pl] == FG_THR_GENERAL) || (m1 > thc[pl]));
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne);
+                if (store) bm[bm_plane_words * pl + (size_t)row * pitchw + (col >> 5)] = m;
+            }
+        } else {
+            for (int pl = 0; pl < n_planes; ++pl) {
+                bool ne = false;
+                if (valid) {
+                    const uint64_t th64 = __ldg(thr_planes + in_stride * pl + pix);
+                    ne = (th64 == FG_THR_GENERAL) || (m1 > th64);
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, ne);
+                if (store) bm[bm_plane_words * pl + (size_t)row * pitchw + (col >> 5)] = m;
+            }
         }
     }
 }

@@ -311,6 +311,35 @@ def test_planes_batched_equals_sequential(ctx):
         assert np.array_equal(outs[c], O.render_pixelwise(lams[c], p, d, off_in))
 
 
+@pytest.mark.parametrize("dist", ["const", "lognorm"])
+@pytest.mark.parametrize("joint", ["1", "0"], ids=["joint", "per-plane"])
+def test_three_plane_table_generation_on_mixed_content(ctx, monkeypatch, dist, joint):
+    """k_gen_rows<., 3> generates a cell row for the three planes from ONE seeding and ONE Knuth chain per cell.  Planes
+    that are equal, black (lambda = 0), saturated (lambda' >= 12: the general sampler, parked from the seed state),
+    dense (several grains per cell: skipped outputs) and independent noise, all in one image; every plane must equal
+    the oracle's render of that plane alone, and the per-plane generator (FG_B200_GEN_JOINT=0) must agree."""
+    monkeypatch.setenv("FG_B200_GEN_JOINT", joint)
+    w, h = 72, 48
+    kw = dict(radius=0.1, n_samples=12)
+    if dist == "lognorm":
+        kw.update(radius_dist=O.DIST_LOGNORM, radius_stddev=0.05)
+    p = O.make_params(algo=O.ALGO_PIXEL, **kw)
+    d, off, off_in = O.derive_common(p, w, h)
+    img = noise_u8(w, h, seed=31)
+    img[:, :, 1] = img[:, :, 0]            # G == R: every cell stops at the same count in both
+    img[:12, :, 2] = 0                     # B black on top ...
+    img[12:24, :, 2] = 255                 # ... saturated below it (general sampler beside Knuth planes)
+    img[24:36, 20:50, :] = 255             # all planes saturated
+    img[36:, :24, 0] = 250                 # dense Knuth cells (lambda' ~ 1.76) beside sparse ones
+    lams = [lambda_from_u8(img[:, :, c], d.inv_e_pi_r2) for c in range(3)]
+    lams[1][40:, 30:40] = np.float32(11.9) / np.float32(d.delta * d.delta)   # lambda' just under the Knuth limit
+    lams[2][40:, 30:40] = np.float32(12.1) / np.float32(d.delta * d.delta)   # ... and just over it
+    outs = ctx.render_planes(fg_params_from(p, d, path=3), 2, lams, off_in)
+    for c in range(3):
+        ref = O.render_pixelwise(lams[c], p, d, off_in)
+        assert np.array_equal(outs[c], ref), f"plane {c}: {np.count_nonzero(outs[c] != ref)} px differ"
+
+
 @pytest.mark.parametrize("mode,algo", [(1, O.ALGO_PIXEL), (0, O.ALGO_PIXEL), (1, O.ALGO_GRAIN), (0, O.ALGO_GRAIN)],
                          ids=["rgb-pixel", "luma-pixel", "rgb-grain", "luma-grain"])
 def test_rgb8_pipeline_matches_oracle(ctx, mode, algo):
