@@ -37,7 +37,7 @@ class FgStats(C.Structure):
                 ("launches", C.c_uint32), ("tiles_total", C.c_uint32), ("tiles_fallback", C.c_uint32),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("strip_ms", C.c_float), ("strip_launches", C.c_uint32),
-                ("table_ms", C.c_float), ("reserved", C.c_uint32)]
+                ("table_ms", C.c_float), ("table_reused", C.c_uint32)]
 
 
 class FghParams(C.Structure):
@@ -76,6 +76,8 @@ ABI = {
     "fg_render_grainwise": (C.c_int, [_VP, _P(FgParams), _VP, _VP, _VP]),
     "fg_render_planes": (C.c_int, [_VP, _P(FgParams), C.c_int, C.c_int, _P(_VP), _VP, _P(_VP)]),
     "fg_render_planes_cancelable": (C.c_int, [_VP, _P(FgParams), C.c_int, C.c_int, _P(_VP), _VP, _P(_VP), _P(C.c_int)]),
+    "fg_set_table_cache": (None, [_VP, C.c_int]),
+    "fg_refine_planes": (C.c_int, [_VP, _P(FgParams), C.c_int, C.c_int, _P(_VP), _VP, C.c_uint32, C.c_uint32, _P(_VP), _P(C.c_int)]),
     "fg_render_planes_device": (C.c_int, [_VP, _P(FgParams), C.c_int, C.c_int, _VP, _VP, _VP, C.c_int]),
     "fg_context_stream": (C.c_uint64, [_VP]),
     "fg_context_synchronize": (C.c_int, [_VP]),

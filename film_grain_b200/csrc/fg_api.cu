@@ -211,7 +211,7 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
         FG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, it, (uint64_t*)ctx->scan_out.p, npix_in, ctx->stream));
         k_total<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->counts.p, (const uint64_t*)ctx->scan_out.p, npix_in, d_total);
         FG_CUDA(ctx, cudaMemcpyAsync(&total, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FG_CUDA(ctx, wait_stream(ctx));
         ctx->stats.launches += 4;
         if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
         if (total >> 32) tiled = false; // the tile kernel indexes a tile's grains with 32 bits
@@ -275,11 +275,18 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
     return FG_OK;
 }
 
-int render_planes_device_locked(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int algo, int n_planes,
+int render_planes_device_locked(fg_ctx* ctx, const fg_params* p, const RenderConsts& c_in, int algo, int n_planes,
                                 const float* d_lambda, const float* d_offsets, float* d_out) {
     int rc = init_tables(ctx);
     if (rc) return rc;
     if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    RenderConsts c = c_in;
+    if (ctx->abort_sent) { // the previous render on this context was stopped inside a launch: lower the word again
+        FG_CUDA(ctx, cudaStreamSynchronize(ctx->abort_stream));
+        FG_CUDA(ctx, cudaMemsetAsync(ctx->d_abort, 0, sizeof(int), ctx->stream));
+        ctx->abort_sent = false;
+    }
+    c.abort = cancel_armed(ctx) ? ctx->d_abort : nullptr; // no flag armed: the kernels do not even look
     if (algo == FG_ALGO_PIXEL) return pixelwise_device(ctx, p, c, n_planes, d_lambda, d_offsets, d_out);
     const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
     for (int pl = 0; pl < n_planes; ++pl) {
@@ -371,17 +378,109 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
     rc = render_planes_device_locked(ctx, p, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, d_dst);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (cancel_armed(ctx)) { // a copy into pageable memory blocks the host until the kernels are done: watch the flag first
+        FG_CUDA(ctx, wait_stream(ctx));
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    }
     const size_t band_off = (size_t)c.row_begin * p->out_w, band_elems = (size_t)(c.row_end - c.row_begin) * p->out_w;
     for (int pl = 0; pl < n_planes && !mapped; ++pl) // mapped: the kernels' own stores were the transfer
         FG_CUDA(ctx, cudaMemcpyAsync(out[pl] + band_off, (float*)ctx->out.p + out_elems * pl + band_off, band_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
-    FG_CUDA(ctx, cudaStreamSynchronize(s));
+    FG_CUDA(ctx, wait_stream(ctx));
     cudaEventElapsedTime(&ctx->stats.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->stats.d2h_ms, ctx->ev[2], ctx->ev[3]);
     ctx->stats.h2d_bytes = (up_elems * n_planes + (size_t)p->n_samples * 2) * sizeof(float);
     ctx->stats.d2h_bytes = band_elems * n_planes * sizeof(float);
     if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    return FG_OK;
+}
+
+
+// ---- progressive refinement (fg_refine_planes) ---------------------------------------------------------------------
+// out = (count_a + count_b) * (1 / (n_a + n_b)) with count = rint(mean * n): exact for the sample counts a render can
+// hold (f32 integers), so the merged image equals one render of all n_a + n_b samples bit for bit.
+__global__ void __launch_bounds__(256) k_refine_merge(float* __restrict__ acc, const float* __restrict__ part, size_t out_elems, size_t band_off,
+                                                       size_t band_elems, int n_planes, float n_acc, float n_part, float inv_total) {
+    const size_t n = band_elems * (size_t)n_planes;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (size_t)gridDim.x * 256) {
+        const size_t pl = t / band_elems, idx = pl * out_elems + band_off + (t - pl * band_elems);
+        const float a = rintf(__fmul_rn(acc[idx], n_acc)), b = rintf(__fmul_rn(part[idx], n_part));
+        acc[idx] = __fmul_rn(__fadd_rn(a, b), inv_total);
+    }
+}
+
+int refine_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda, const float* offsets,
+                       uint32_t k_begin, uint32_t k_end, float* const* out, const volatile int* cancel) {
+    if (!ctx) return FG_ERR_INVALID;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ScopedCallCancel call_cancel(ctx, cancel);
+    ScopedDevice dev(ctx->device);
+    ctx->err.clear();
+    ctx->stats = fg_stats{};
+    ctx->fb_pending = false;
+    int rc = validate(ctx, p);
+    if (rc) return rc;
+    if (algo != FG_ALGO_PIXEL && algo != FG_ALGO_GRAIN) return set_err(ctx, FG_ERR_INVALID, "algo must be FG_ALGO_PIXEL or FG_ALGO_GRAIN");
+    if (n_planes < 1 || n_planes > 16) return set_err(ctx, FG_ERR_INVALID, "n_planes must be in 1..16");
+    if (!lambda || !offsets || !out) return set_err(ctx, FG_ERR_INVALID, "NULL buffer");
+    for (int pl = 0; pl < n_planes; ++pl)
+        if (!lambda[pl] || !out[pl]) return set_err(ctx, FG_ERR_INVALID, "NULL plane pointer");
+    if (!(k_begin < k_end && k_end <= p->n_samples)) return set_err(ctx, FG_ERR_INVALID, "sample slice must satisfy k_begin < k_end <= n_samples");
+    if ((rc = check_offsets(ctx, p, offsets))) return rc;
+    // the extents of ALL n_samples offsets size the cell rectangle, so every slice of a refinement asks for the same table
+    RenderConsts c = make_consts(p, offsets);
+    fg_params pp = *p;
+    pp.n_samples = k_end - k_begin;
+    c.n = pp.n_samples;
+    c.inv_samples = 1.0f / (float)pp.n_samples;
+    auto& pg = ctx->prog;
+    if (k_begin > 0 && !(pg.valid && pg.k == k_begin && pg.algo == algo && pg.n_planes == (uint32_t)n_planes && pg.out_w == p->out_w &&
+                         pg.out_h == p->out_h && pg.row_begin == (uint32_t)c.row_begin && pg.row_end == (uint32_t)c.row_end))
+        return set_err(ctx, FG_ERR_INVALID, "fg_refine_planes: k_begin > 0 continues the previous refinement of this context, which ended elsewhere");
+    pg.valid = false;
+    const size_t in_elems = (size_t)p->in_w * p->in_h, out_elems = (size_t)p->out_w * p->out_h;
+    if ((rc = ensure(ctx, ctx->lambda, in_elems * n_planes * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->acc, out_elems * n_planes * sizeof(float)))) return rc;
+    if (k_begin && (rc = ensure(ctx, ctx->part, out_elems * n_planes * sizeof(float)))) return rc;
+    if ((rc = ensure(ctx, ctx->offsets, (size_t)pp.n_samples * 2 * sizeof(float)))) return rc;
+    cudaStream_t s = ctx->stream;
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+    int in_r0, in_r1;
+    input_rows_of_band(p, c, algo, in_r0, in_r1);
+    const size_t up_off = (size_t)in_r0 * p->in_w, up_elems = (size_t)(in_r1 - in_r0) * p->in_w;
+    for (int pl = 0; pl < n_planes; ++pl)
+        FG_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lambda.p + in_elems * pl + up_off, lambda[pl] + up_off, up_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    FG_CUDA(ctx, cudaMemcpyAsync(ctx->offsets.p, offsets + 2 * (size_t)k_begin, (size_t)pp.n_samples * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+    float* const d_dst = k_begin ? (float*)ctx->part.p : (float*)ctx->acc.p;
+    rc = render_planes_device_locked(ctx, &pp, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, d_dst);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    const size_t band_off = (size_t)c.row_begin * p->out_w, band_elems = (size_t)(c.row_end - c.row_begin) * p->out_w;
+    if (k_begin) {
+        const unsigned blocks = (unsigned)std::min<size_t>((band_elems * n_planes + 255) / 256, (size_t)ctx->sm_count * 16);
+        k_refine_merge<<<blocks, 256, 0, s>>>((float*)ctx->acc.p, (const float*)ctx->part.p, out_elems, band_off, band_elems, n_planes,
+                                              (float)k_begin, (float)pp.n_samples, 1.0f / (float)k_end);
+        FG_CUDA(ctx, cudaGetLastError());
+        ctx->stats.launches += 1;
+    }
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (cancel_armed(ctx)) {
+        FG_CUDA(ctx, wait_stream(ctx));
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    }
+    for (int pl = 0; pl < n_planes; ++pl)
+        FG_CUDA(ctx, cudaMemcpyAsync(out[pl] + band_off, (float*)ctx->acc.p + out_elems * pl + band_off, band_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
+    FG_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+    FG_CUDA(ctx, wait_stream(ctx));
+    cudaEventElapsedTime(&ctx->stats.h2d_ms, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&ctx->stats.d2h_ms, ctx->ev[2], ctx->ev[3]);
+    ctx->stats.h2d_bytes = (up_elems * n_planes + (size_t)pp.n_samples * 2) * sizeof(float);
+    ctx->stats.d2h_bytes = band_elems * n_planes * sizeof(float);
+    if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    pg.valid = true; pg.k = k_end; pg.algo = algo; pg.n_planes = (uint32_t)n_planes; pg.out_w = p->out_w; pg.out_h = p->out_h;
+    pg.row_begin = (uint32_t)c.row_begin; pg.row_end = (uint32_t)c.row_end;
     return FG_OK;
 }
 
@@ -632,6 +731,16 @@ int fg_context_create(fg_ctx** out, int device) {
         return FG_ERR_CUDA_STICKY;
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    // in-launch cancel (fg_ctx.cuh: wait_stream); without these the flag is still honoured between the stages
+    if (cudaStreamCreateWithFlags(&ctx->abort_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->d_abort, sizeof(int)) != cudaSuccess || cudaMemset(ctx->d_abort, 0, sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc((void**)&ctx->h_one, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        if (ctx->d_abort) cudaFree(ctx->d_abort);
+        ctx->d_abort = nullptr;
+    }
+    if (ctx->h_one) *ctx->h_one = 1;
     int rc = tile_setup(ctx);
     if (!rc && cudaFuncSetAttribute(k_gw_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GwTileSmem)) != cudaSuccess) {
         cudaGetLastError();
@@ -686,9 +795,13 @@ void fg_context_destroy(fg_ctx* ctx) {
         ScopedDevice dev(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         for (DevBuf* b : {&ctx->lambda, &ctx->out, &ctx->offsets, &ctx->bits, &ctx->counts, &ctx->scan_out, &ctx->scan_tmp,
-                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->bitmap, &ctx->rowinfo, &ctx->ptab, &ctx->gtab, &ctx->fbtotal, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut, &ctx->gw_states})
+                          &ctx->grains, &ctx->misc, &ctx->tiles, &ctx->thr, &ctx->bitmap, &ctx->rowinfo, &ctx->ptab, &ctx->gtab, &ctx->fbtotal, &ctx->rgb_in, &ctx->rgb_out, &ctx->chroma, &ctx->lut, &ctx->gw_states, &ctx->acc, &ctx->part})
             release(*b);
         for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+        if (ctx->abort_stream) { cudaStreamSynchronize(ctx->abort_stream); cudaStreamDestroy(ctx->abort_stream); }
+        if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
+        if (ctx->d_abort) cudaFree(ctx->d_abort);
+        if (ctx->h_one) cudaFreeHost(ctx->h_one);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         cudaGetLastError();
     }
@@ -754,6 +867,23 @@ int fg_render_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, co
     return render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out);
 }
 
+int fg_refine_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda, const float* offsets,
+                     uint32_t k_begin, uint32_t k_end, float* const* out, const volatile int* cancel) {
+    // a multi-device context refines on its first device (a preview path: one frame, one GPU)
+    fg_ctx* c1 = (ctx && !ctx->subs.empty()) ? ctx->subs[0] : ctx;
+    const int rc = refine_planes_host(c1, p, algo, n_planes, lambda, offsets, k_begin, k_end, out, cancel ? cancel : (ctx ? ctx->cancel : nullptr));
+    if (c1 != ctx && rc) ctx->err = c1->err;
+    return rc;
+}
+
+void fg_set_table_cache(fg_ctx* ctx, int enable) {
+    if (!ctx) return;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    for (fg_ctx* sc : ctx->subs) fg_set_table_cache(sc, enable);
+    ctx->tcache.enabled = enable != 0;
+    if (!enable) ctx->tcache.valid = false;
+}
+
 int fg_render_planes_cancelable(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
                                 const float* offsets, float* const* out, const volatile int* cancel) {
     if (ctx && !ctx->subs.empty()) return multi_render_planes_host(ctx, p, algo, n_planes, lambda, offsets, out, cancel);
@@ -785,8 +915,9 @@ int fg_render_planes_device(fg_ctx* ctx, const fg_params* p, int algo, int n_pla
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (stream_sync) {
-        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FG_CUDA(ctx, wait_stream(ctx));
         cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
     }
     return FG_OK;
 }

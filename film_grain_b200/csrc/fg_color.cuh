@@ -172,8 +172,9 @@ int color_render_device(fg_ctx* ctx, const fg_params* p, int algo, int color_mod
     if (rc) { cudaStreamSynchronize(ctx->stream); return rc; }
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (stream_sync) {
-        FG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        FG_CUDA(ctx, wait_stream(ctx));
         cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
     }
     return FG_OK;
 }
@@ -196,10 +197,14 @@ int color_render_host(fg_ctx* ctx, const fg_params* p, int algo, int color_mode,
                                   (uint8_t*)ctx->rgb_out.p);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+    if (cancel_armed(ctx)) { // the copy into pageable memory would block the host until the kernels are done
+        FG_CUDA(ctx, wait_stream(ctx));
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+    }
     const size_t band_off = (size_t)c.row_begin * p->out_w * 3, band_bytes = (size_t)(c.row_end - c.row_begin) * p->out_w * 3;
     FG_CUDA(ctx, cudaMemcpyAsync(rgb_out + band_off, (uint8_t*)ctx->rgb_out.p + band_off, band_bytes, cudaMemcpyDeviceToHost, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
-    FG_CUDA(ctx, cudaStreamSynchronize(s));
+    FG_CUDA(ctx, wait_stream(ctx));
     cudaEventElapsedTime(&ctx->stats.h2d_ms, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&ctx->stats.kernel_ms, ctx->ev[1], ctx->ev[2]);
     cudaEventElapsedTime(&ctx->stats.d2h_ms, ctx->ev[2], ctx->ev[3]);

@@ -3,6 +3,7 @@
 #pragma once
 #include "../../include/fg.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +25,27 @@ struct DevBuf {
 
 } // namespace
 
+// Identity of a cell table (fg_set_table_cache): everything the table's contents depend on.  N, the sample offsets and
+// the zoom are NOT part of it -- they only decide which cells a render visits, i.e. the rectangle the table must cover.
+struct TableKey {
+    uint64_t seed_cell = 0, h0 = 0, h1 = 0;   // h0, h1: 128-bit content hash of the lambda planes
+    uint32_t seeding = 0, in_w = 0, in_h = 0, n_planes = 0, lognorm = 0;
+    float delta = 0, rm = 0, mean_linear = 0;
+    double mu = 0, sigma = 0, slack = 0;
+    bool operator==(const TableKey& o) const {
+        return seed_cell == o.seed_cell && h0 == o.h0 && h1 == o.h1 && seeding == o.seeding && in_w == o.in_w && in_h == o.in_h &&
+               n_planes == o.n_planes && lognorm == o.lognorm && delta == o.delta && rm == o.rm && mean_linear == o.mean_linear &&
+               mu == o.mu && sigma == o.sigma && slack == o.slack;
+    }
+};
+struct TableCache {
+    bool enabled = false, valid = false;
+    TableKey key;
+    int i0 = 0, j0 = 0, cols = 0, rows = 0; // cell rectangle of the table held in the ptab / gtab / rowinfo / bitmap / thr pools
+    uint64_t total = 0;                     // grain slots (sum of the row capacities)
+    double dens = 0.0;
+};
+
 struct fg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -36,12 +58,22 @@ struct fg_ctx {
     int sm_count = 0;
     size_t smem_optin = 0;
     // pools
-    DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, bitmap, rowinfo, ptab, gtab, fbtotal, rgb_in, rgb_out, chroma, lut, gw_states;
+    DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, bitmap, rowinfo, ptab, gtab, fbtotal, rgb_in, rgb_out, chroma, lut, gw_states, acc, part;
     bool tables_ready = false;
     uint32_t fb_count_host = 0; // tiled path: fallback-list length of the last render (valid after a stream sync)
     bool fb_pending = false;
     size_t table_max = (size_t)48 << 30; // cell-table budget per band (FG_B200_TABLE_MAX_BYTES overrides; tests)
     double table_slack_sigma = 8.0; // row capacity = expected grains + this many sigma + 64 (FG_B200_TABLE_SLACK_SIGMA: tests)
+    // in-launch cancel: a device word the kernels poll (RenderConsts::abort), raised from `abort_stream` by the host
+    // thread that waits for the render (wait_stream) when it sees the caller's cancel flag
+    int* d_abort = nullptr;
+    int* h_one = nullptr; // page-locked 1: the source of the abort copy
+    cudaStream_t abort_stream = nullptr;
+    cudaEvent_t ev_wait = nullptr;
+    bool abort_sent = false;
+    TableCache tcache;
+    // progressive refinement (fg_refine_planes): `acc` holds the render of samples [0, acc_k) of the geometry below
+    struct { bool valid = false; uint32_t k = 0, n_planes = 0, out_w = 0, out_h = 0, row_begin = 0, row_end = 0; int algo = 0; } prog;
     const char* eval_kernel = ""; // name of the kernel that evaluated / rasterised the last render (fg_last_eval_kernel)
     uint32_t strip_launches = 0;
     // multi-device context (fg_context_create_multi): this object only routes; subs[g] is a complete context on its own
@@ -114,6 +146,25 @@ bool cancelled(const fg_ctx* ctx) {
     return (ctx->cancel && *ctx->cancel != 0) || (ctx->call_cancel && *ctx->call_cancel != 0);
 }
 bool cancel_armed(const fg_ctx* ctx) { return ctx->cancel || ctx->call_cancel; }
+
+// Wait for the context's stream.  With a cancel flag armed the host polls instead of blocking: the moment the caller's
+// flag goes up, the device word the kernels test is raised from a second stream (a 4-byte copy that overtakes the
+// running kernels), so a render stops within one CTA lifetime (~1.5 ms on a 4K frame) instead of at the next call
+// boundary.  The caller checks cancelled() afterwards.
+cudaError_t wait_stream(fg_ctx* ctx) {
+    if (!cancel_armed(ctx) || !ctx->d_abort) return cudaStreamSynchronize(ctx->stream);
+    cudaError_t e = cudaEventRecord(ctx->ev_wait, ctx->stream);
+    if (e != cudaSuccess) return e;
+    for (;;) {
+        e = cudaEventQuery(ctx->ev_wait);
+        if (e != cudaErrorNotReady) return e;
+        if (!ctx->abort_sent && cancelled(ctx)) {
+            cudaMemcpyAsync(ctx->d_abort, ctx->h_one, sizeof(int), cudaMemcpyHostToDevice, ctx->abort_stream);
+            ctx->abort_sent = true;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+}
 
 // the per-call cancel flag lives in the context only while the call holds the context mutex
 struct ScopedCallCancel {

@@ -55,6 +55,7 @@ k_gw_tile(const GrainRec* __restrict__ grains, const uint64_t* __restrict__ excl
     extern __shared__ __align__(16) unsigned char smem_raw[];
     GwTileSmem& sm = *reinterpret_cast<GwTileSmem*>(smem_raw);
     const int tid = threadIdx.x;
+    if (cta_aborted(c)) return;
     const int tx0 = (int)(blockIdx.x % (unsigned)tiles_x) * FG_GT_W, ty0 = c.row_begin + (int)(blockIdx.x / (unsigned)tiles_x) * FG_GT_H;
     const int tx1 = min(tx0 + FG_GT_W, c.out_w), ty1 = min(ty0 + FG_GT_H, c.row_end); // exclusive
     const uint64_t total = *n_grains_ptr;

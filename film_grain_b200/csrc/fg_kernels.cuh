@@ -23,7 +23,20 @@ struct RenderConsts {
     int row_begin, row_end; // output row band
     // extreme sample offsets (tiled path window sizing)
     float off_min_x, off_max_x, off_min_y, off_max_y;
+    // Cooperative cancel INSIDE a launch (render_with_input_image_cancelable, src/lib.rs:116-132; the viewer's
+    // latest-job-wins worker, src/bin/viewer.rs:975-1028): a device word the host raises from a second stream while the
+    // kernels run; CTAs that start after that return at once.  nullptr (no cancel flag armed): no check at all.
+    const int* abort;
 };
+
+// CTA-uniform: every thread reads the word, the barrier ORs the verdicts (threads may read either side of the host's store)
+__device__ __forceinline__ bool cta_aborted(const RenderConsts& c) {
+    return c.abort != nullptr && __syncthreads_or(*(const volatile int*)c.abort != 0) != 0;
+}
+// warp-uniform variant for kernels whose warps work independently
+__device__ __forceinline__ bool warp_aborted(const RenderConsts& c) {
+    return c.abort != nullptr && __any_sync(0xFFFFFFFFu, *(const volatile int*)c.abort != 0);
+}
 
 // Plane::get_clamped (src/model.rs:60-67) at the cell->pixel mapping of src/pixelwise.rs:69-73
 __device__ __forceinline__ float lambda_of_cell(const float* __restrict__ lambda, const RenderConsts& c,
@@ -73,6 +86,7 @@ __device__ inline bool indicator_direct(const float* __restrict__ lambda, const 
 __global__ void __launch_bounds__(256) k_pixelwise_direct(const float* __restrict__ lambda, size_t lambda_stride,
                                                            const float2* __restrict__ offsets_input,
                                                            float* __restrict__ out, size_t out_stride, RenderConsts c) {
+    if (cta_aborted(c)) return;
     int x = blockIdx.x * 32 + threadIdx.x;
     int y = c.row_begin + blockIdx.y * 8 + threadIdx.y;
     if (x >= c.out_w || y >= c.row_end) return;
@@ -103,6 +117,7 @@ __global__ void __launch_bounds__(256) k_pixelwise_direct_tiles(const float* __r
     const uint64_t work = (uint64_t)nt * chunks_per_tile;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (uint64_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
+        if (c.abort != nullptr && *(const volatile int*)c.abort != 0) return; // cancelled (no barriers below: threads may leave alone)
         const TileRef t = tiles[wi / chunks_per_tile];
         const int yl = (int)(wi % chunks_per_tile) * 8 + ty;
         if (yl >= t.h || tx >= t.w) continue;
@@ -294,6 +309,7 @@ __global__ void __launch_bounds__(256) k_gw_splat(const GrainRec* __restrict__ g
                                                    const float2* __restrict__ offsets, uint32_t* __restrict__ bits,
                                                    uint32_t lanes32, RenderConsts c) {
     __shared__ float2 s_off[FG_GW_OFF_CHUNK + 1];
+    if (cta_aborted(c)) return;
     const uint64_t total = *n_grains_ptr;
     const int last_x = c.out_w - 1, lo_y = c.row_begin, hi_y = c.row_end - 1;
     const IDX xstep = (IDX)lanes32, ystep = (IDX)c.out_w * (IDX)lanes32;

@@ -378,6 +378,44 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         const float rcl = c.rad.mean_linear > c.rad.rm ? c.rad.rm : c.rad.mean_linear;
         g.r2c = rcl * rcl;
     }
+    // ---- table cache (fg_set_table_cache; the viewer's re-render after an N / sigma / zoom change, src/bin/viewer.rs:944-1067):
+    // a whole-frame staged render whose table identity equals the cached one and whose cell rectangle lies inside the
+    // cached rectangle evaluates from the table in the pools; otherwise the table is built over a rectangle with a margin
+    // (so that a somewhat larger sigma or a smaller zoom still fits) and remembered.
+    TableCache& tc = ctx->tcache;
+    const bool use_cache = staged && tc.enabled && c.row_begin == 0 && c.row_end == (int)p->out_h;
+    bool reuse = false;
+    TableKey key{};
+    if (use_cache) {
+        int rc0;
+        if ((rc0 = ensure(ctx, ctx->misc, 64))) return rc0;
+        unsigned long long* d_h = (unsigned long long*)ctx->misc.p + 2;
+        unsigned long long hh[2] = {0, 0};
+        FG_CUDA(ctx, cudaMemsetAsync(d_h, 0, 16, ctx->stream));
+        k_hash_planes<<<(unsigned)std::min<size_t>((n_in + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(d_lambda, n_in, d_h);
+        FG_CUDA(ctx, cudaGetLastError());
+        FG_CUDA(ctx, cudaMemcpyAsync(hh, d_h, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, wait_stream(ctx));
+        ctx->stats.launches += 1;
+        key.seed_cell = c.seed_cell; key.h0 = hh[0]; key.h1 = hh[1];
+        key.seeding = c.seeding; key.in_w = p->in_w; key.in_h = p->in_h; key.n_planes = (uint32_t)n_planes; key.lognorm = c.rad.lognorm;
+        key.delta = p->delta; key.rm = c.rad.rm; key.mean_linear = c.rad.mean_linear; key.mu = c.rad.mu; key.sigma = c.rad.sigma;
+        key.slack = ctx->table_slack_sigma;
+        reuse = tc.valid && key == tc.key && tc.i0 <= g.bm_i0 && tc.j0 <= g.bm_j0 &&
+                (long long)tc.i0 + tc.cols >= (long long)g.bm_i0 + g.bm_cols && (long long)tc.j0 + tc.rows >= (long long)g.bm_j0 + g.bm_rows;
+        if (reuse) {
+            g.bm_i0 = tc.i0; g.bm_j0 = tc.j0; g.bm_cols = tc.cols; g.bm_rows = tc.rows;
+        } else { // margin: one input pixel + half the largest offset, in cells, on every side
+            const double moff = std::max(std::max(std::fabs((double)c.off_min_x), std::fabs((double)c.off_max_x)),
+                                         std::max(std::fabs((double)c.off_min_y), std::fabs((double)c.off_max_y)));
+            const int extra = (int)std::min(4096.0, std::ceil((1.0 + 0.5 * moff) / (double)p->delta));
+            g.bm_i0 -= extra; g.bm_j0 -= extra; g.bm_cols += 2 * extra; g.bm_rows += 2 * extra;
+        }
+        g.bm_pitchw = (uint32_t)((g.bm_cols + 31) / 32);
+        g.ppitch = (uint32_t)((g.bm_cols + 1 + 7) / 8 * 8);
+    }
+    if (!reuse) tc.valid = false; // the pools are about to be rewritten (or are not a whole-frame staged table)
+    ctx->stats.table_reused = reuse ? 1u : 0u;
     const size_t bm_plane_words = (size_t)g.bm_rows * g.bm_pitchw;
     if (bm_plane_words * (size_t)n_planes * 4 > ((size_t)12 << 30) || g.bm_pitchw * 32u / 256u + 1u > 65535u) return 1;
     const size_t n_rows_all = (size_t)g.bm_rows * n_planes;
@@ -400,10 +438,10 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     const int iy1 = std::min(std::max((int)std::floor((double)(g.bm_j0 + g.bm_rows) * (double)p->delta) + 1, 0), (int)p->in_h - 1);
     const size_t thr_first = (size_t)iy0 * p->in_w, thr_n = (size_t)(iy1 - iy0 + 1) * p->in_w;
     const unsigned tb = (unsigned)std::min<size_t>((thr_n + 255) / 256, (size_t)ctx->sm_count * 16);
-    k_thresholds<<<dim3(tb, (unsigned)n_planes), 256, 0, s>>>(d_lambda, in_stride, thr_first, thr_n, p->delta, d_thr, d_e);
+    if (!reuse) k_thresholds<<<dim3(tb, (unsigned)n_planes), 256, 0, s>>>(d_lambda, in_stride, thr_first, thr_n, p->delta, d_thr, d_e);
     FG_CUDA(ctx, cudaGetLastError());
     uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
-    {
+    if (!reuse) {
         dim3 bgrid((unsigned)((g.bm_rows + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
 #define FG_LAUNCH_BM(SD, NPL)                                                                                       \
     k_first_draw_bitmap<SD, NPL><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, \
@@ -417,8 +455,8 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         }
 #undef FG_LAUNCH_BM
         FG_CUDA(ctx, cudaGetLastError());
+        ctx->stats.launches += 2;
     }
-    ctx->stats.launches += 2;
     CellTable tab{};
     double table_dens = 0.0;
     if (staged) {
@@ -434,14 +472,17 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         uint64_t* d_rowbase = (uint64_t*)((unsigned char*)ctx->rowinfo.p + s_bytes);
         uint32_t* d_rowcap = (uint32_t*)((unsigned char*)d_rowbase + (base_bytes + 255) / 256 * 256);
         uint32_t* d_overflow = (uint32_t*)((unsigned char*)d_rowcap + (cap_bytes + 63) / 64 * 64);
-        k_row_expect<<<dim3((unsigned)(iy1 - iy0 + 1), n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, iy0, d_S, c);
-        FG_CUDA(ctx, cudaGetLastError());
-        k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, ctx->table_slack_sigma, d_rowbase, d_rowcap, c);
-        FG_CUDA(ctx, cudaGetLastError());
-        FG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 4, s));
-        uint64_t total = 0;
-        FG_CUDA(ctx, cudaMemcpyAsync(&total, d_rowbase + n_rows_all, 8, cudaMemcpyDeviceToHost, s));
-        FG_CUDA(ctx, cudaStreamSynchronize(s));
+        uint64_t total = tc.total;
+        if (!reuse) {
+            k_row_expect<<<dim3((unsigned)(iy1 - iy0 + 1), n_planes), 256, 0, s>>>(d_lambda, in_stride, g.bm_i0, g.bm_cols, iy0, d_S, c);
+            FG_CUDA(ctx, cudaGetLastError());
+            k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, ctx->table_slack_sigma, d_rowbase, d_rowcap, c);
+            FG_CUDA(ctx, cudaGetLastError());
+            FG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 4, s));
+            FG_CUDA(ctx, cudaMemcpyAsync(&total, d_rowbase + n_rows_all, 8, cudaMemcpyDeviceToHost, s));
+            FG_CUDA(ctx, wait_stream(ctx));
+            if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+        }
         const size_t bpg = c.rad.lognorm ? 14 : 10;
         if (total == 0xFFFFFFFFFFFFFFFFULL || total * bpg + pg_bytes > ctx->table_max) return 2;
         const size_t g_bytes = ((size_t)total * 8 + 255) / 256 * 256;
@@ -454,6 +495,7 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         float* d_R2 = (float*)((unsigned char*)ctx->gtab.p + g_bytes);
         uint16_t* d_C = (uint16_t*)((unsigned char*)ctx->gtab.p + g_bytes + r2_bytes);
         StageGeo geo{g.bm_i0, g.bm_j0, g.bm_cols, g.bm_rows, g.bm_pitchw, g.ppitch};
+        if (!reuse) {
         // three planes: one warp generates a cell row for all of them (one seeding and one Knuth chain per cell)
         const bool joint = n_planes == 3 && !(std::getenv("FG_B200_GEN_JOINT") && std::atoi(std::getenv("FG_B200_GEN_JOINT")) == 0);
         const size_t gwarps = joint ? (size_t)g.bm_rows : n_rows_all;
@@ -467,9 +509,11 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         FG_CUDA(ctx, cudaGetLastError());
         uint32_t overflow = 0;
         FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));
-        FG_CUDA(ctx, cudaStreamSynchronize(s));
+        FG_CUDA(ctx, wait_stream(ctx));
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
         ctx->stats.launches += 3;
         if (overflow) return 3; // a row outgrew its expected size + 8 sigma (or a cell holds > 65535 grains): regenerate in-kernel instead
+        }
         tab.Pg = (const uint32_t*)ctx->ptab.p;
         tab.rowbase = d_rowbase;
         tab.Gg = d_G;
@@ -479,6 +523,11 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
             const double cap_row = (double)total / (double)n_rows_all, k = ctx->table_slack_sigma;
             const double rt = (-k + std::sqrt(k * k + 4.0 * std::max(cap_row - 64.0, 0.0))) * 0.5;
             table_dens = rt * rt / (double)g.bm_cols;
+        }
+        if (use_cache) { // the pools now hold this table
+            tc.valid = true; tc.key = key;
+            tc.i0 = g.bm_i0; tc.j0 = g.bm_j0; tc.cols = g.bm_cols; tc.rows = g.bm_rows;
+            tc.total = total; tc.dens = table_dens;
         }
     }
     const float2* off = (const float2*)d_offsets;

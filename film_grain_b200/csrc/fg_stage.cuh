@@ -94,6 +94,25 @@ __global__ void __launch_bounds__(1024) k_row_bases(const double* __restrict__ S
     if (bad && threadIdx.x == 0) rowbase[n] = 0xFFFFFFFFFFFFFFFFULL;
 }
 
+// 128-bit content hash of the lambda planes (two position-keyed splitmix sums, so the launch geometry does not matter):
+// the identity of a cached cell table.  acc[0], acc[1] are zeroed by the caller.
+__global__ void __launch_bounds__(256) k_hash_planes(const float* __restrict__ v, size_t n, unsigned long long* __restrict__ acc) {
+    uint64_t a = 0, b = 0;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (size_t)gridDim.x * 256) {
+        const uint64_t x = (uint64_t)__float_as_uint(__ldg(v + t));
+        a += splitmix64(x ^ ((uint64_t)t * 0xD6E8FEB86659FD93ULL));
+        b += splitmix64((x << 32 | x) + rotl64((uint64_t)t + 0x2545F4914F6CDD1DULL, 29));
+    }
+    for (int d = 16; d; d >>= 1) {
+        a += __shfl_down_sync(0xFFFFFFFFu, a, d);
+        b += __shfl_down_sync(0xFFFFFFFFu, b, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(acc, (unsigned long long)a);
+        atomicAdd(acc + 1, (unsigned long long)b);
+    }
+}
+
 struct StageGeo {
     int i0, j0, cols, rows;   // cell rectangle of the band (same as the first-draw bitmap)
     uint32_t pitchw;          // bitmap words per row
@@ -145,6 +164,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
     GenWarpSmem<NPL>& sm = sm_all[warp];
     const size_t widx0 = (size_t)blockIdx.x * FG_GW_WARPS + warp;
     if (widx0 >= (size_t)geo.rows * (NPL == 1 ? n_planes : 1)) return; // whole warp
+    if (warp_aborted(c)) return;
     const int plane0 = NPL == 1 ? (int)(widx0 / geo.rows) : 0, row = (int)(widx0 - (size_t)plane0 * geo.rows);
     const int j = geo.j0 + row;
     const float sy = __fmul_rn(__int2float_rn(j), c.delta);

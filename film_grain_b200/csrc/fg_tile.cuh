@@ -80,6 +80,7 @@ template <int SEEDING, int NP> // compile-time seeding variant and plane count (
 __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __restrict__ thr_planes, size_t in_stride,
                                                             int n_planes, uint32_t* __restrict__ bm, size_t bm_plane_words,
                                                             int i0, int j0, int cols, int rows, uint32_t pitchw, RenderConsts c) {
+    if (cta_aborted(c)) return;
     const int col = blockIdx.y * 256 + threadIdx.x;
     const int row0 = blockIdx.x * FG_BM_ROWS;
     const bool valid = col < cols;
@@ -320,6 +321,7 @@ k_pixelwise_strip(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
     uint32_t* extb = rowA + (3 * cfg.RH + 3) / 4 * 4;                // STAGED: [RH][4] prefetched {Pg[first], Pg[last], rowbase lo, hi} of the next step's rows
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (cta_aborted(c)) return; // a cancelled render
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int unit = blockIdx.x;
     const int strip = unit % cfg.n_strips;
@@ -1022,6 +1024,7 @@ __global__ void __launch_bounds__(256) k_pixelwise_table_tiles(const float* __re
     const float rm = c.rad.rm, delta = c.delta, r2c = cfg.r2c;
     const bool radius_ok = LOGN || (c.rad.mean_linear > rm ? rm : c.rad.mean_linear) > 0.0f; // the radius itself: r2c is positive for r < 0
     for (uint64_t wi = blockIdx.x; wi < work; wi += gridDim.x) {
+        if (c.abort != nullptr && *(const volatile int*)c.abort != 0) return; // cancelled (no barriers below: threads may leave alone)
         const TileRef t = tiles[wi / chunks_per_tile];
         const int yl = (int)(wi % chunks_per_tile) * 8 + ty;
         if (yl >= t.h || tx >= t.w) continue;

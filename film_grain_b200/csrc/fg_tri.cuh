@@ -241,6 +241,7 @@ k_pixelwise_tri(const float* __restrict__ lambda, size_t in_stride, const float2
     constexpr uint32_t HBROW = ((uint32_t)NE * SPW * 4u + 127u) / 128u * 128u; // bytes of one coverage row: one word per sample, padded to whole 32-word blocks (the padding stays zero)
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (cta_aborted(c)) return; // a cancelled render: the remaining CTAs of the launch drain in microseconds
     const int unit = blockIdx.x;
     const int strip = unit % cfg.n_strips;
     const int seg = (unit / cfg.n_strips) % cfg.n_segs;

@@ -166,6 +166,28 @@ class Context:
         self._check(self._lib.fg_measure_issue_peak(self._h, out))
         return {"ffma": out[0], "imad": out[1], "imad_lop3_mix": out[2], "dfma": out[3]}
 
+    # -- viewer-grade re-render (src/bin/viewer.rs:944-1067) ---------------------
+    def set_table_cache(self, enable: bool):
+        """Keep the cell table of the last whole-frame pixel-wise render; later renders that differ only in
+        n_samples / offsets / zoom evaluate from it (stats().table_reused == 1)."""
+        self._lib.fg_set_table_cache(self._h, 1 if enable else 0)
+
+    def refine_planes(self, p: FgParams, algo: int, lams, offsets: np.ndarray, k_begin: int, k_end: int, outs=None,
+                      cancel: C.c_int | None = None):
+        """Render samples [k_begin, k_end) of the p.n_samples offsets and merge them into the running image: `outs`
+        then equals a render of the first k_end samples bit for bit (fg_refine_planes)."""
+        lams = [np.ascontiguousarray(a, np.float32) for a in lams]
+        off = np.ascontiguousarray(offsets, np.float32)
+        assert off.shape == (p.n_samples, 2)
+        n = len(lams)
+        if outs is None:
+            outs = [np.zeros((p.out_h, p.out_w), np.float32) for _ in range(n)]
+        lp = (C.c_void_p * n)(*[a.ctypes.data for a in lams])
+        op = (C.c_void_p * n)(*[a.ctypes.data for a in outs])
+        self._check(self._lib.fg_refine_planes(self._h, C.byref(p), algo, n, lp, _ptr(off), k_begin, k_end, op,
+                                               C.byref(cancel) if cancel is not None else None))
+        return outs
+
     def set_cancel_flag(self, flag: C.c_int | None):
         self._cancel = flag  # keep alive
         self._lib.fg_set_cancel_flag(self._h, C.byref(flag) if flag is not None else None)

@@ -102,7 +102,7 @@ typedef struct fg_stats {
     float strip_ms;           /* pixel-wise tiled path: device time of the (last) strip-kernel launch; grain-wise: of the rasterisation (last plane) */
     uint32_t strip_launches;  /*   strip-kernel launches of the call (row sub-bands; normally 1) */
     float table_ms;           /*   device time of the (last) band's thresholds + bitmap + cell-table kernels; grain-wise: grain generation */
-    uint32_t reserved;
+    uint32_t table_reused;    /* 1: the render evaluated from the context's cached cell table (fg_set_table_cache), no table pass */
 } fg_stats;
 
 int fg_abi_version(void);
@@ -129,7 +129,9 @@ const char* fg_last_error(const fg_ctx* ctx);
  * "k_pixelwise_skew", "k_pixelwise_strip", "k_pixelwise_direct", "k_gw_tile", "k_gw_splat + k_gw_reduce"
  * (measurement labels; static storage). */
 const char* fg_last_eval_kernel(const fg_ctx* ctx);
-/* Optional cooperative cancel: *flag != 0 is polled between kernel waves. NULL disables. */
+/* Optional cooperative cancel: *flag != 0 is polled by the host thread that waits for the render and forwarded to a
+ * device word every CTA tests when it starts, so a render stops INSIDE a kernel launch (a 4K frame within ~2 ms), not
+ * only between stages -> FG_ERR_CANCELLED; the output is then undefined. NULL disables (and removes the test). */
 void fg_set_cancel_flag(fg_ctx* ctx, const volatile int* flag);
 /* Statistics of the last render call on this context. */
 void fg_get_stats(const fg_ctx* ctx, fg_stats* out);
@@ -156,12 +158,33 @@ int fg_render_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes,
                      const float* const* lambda, const float* offsets, float* const* out);
 
 /* Same call with a PER-CALL cancel flag (render_with_input_image_cancelable, src/lib.rs:116-132): *cancel != 0
- * is polled between the stages and row sub-bands of the render -> FG_ERR_CANCELLED.  The pointer is used only
+ * is polled between the stages and row sub-bands of the render and inside its launches (see fg_set_cancel_flag) -> FG_ERR_CANCELLED.  The pointer is used only
  * for the duration of this call (unlike fg_set_cancel_flag, which stays registered), so concurrent callers of
  * a shared context cannot overwrite or outlive each other's flags.  cancel == NULL: identical to fg_render_planes. */
 int fg_render_planes_cancelable(fg_ctx* ctx, const fg_params* p, int algo, int n_planes,
                                 const float* const* lambda, const float* offsets, float* const* out,
                                 const volatile int* cancel);
+
+/* ---- Viewer-grade re-render (the reference's interactive caller is src/bin/viewer.rs:944-1067: a worker
+ * that re-renders on every parameter change, latest job wins, CancelToken polled inside the integrators) -------------
+ *
+ * fg_set_table_cache(ctx, 1): the context keeps the cell table of its last whole-frame pixel-wise render.  A later
+ * render whose table identity is the same -- seed, seeding, delta, radius model, plane count and the CONTENT of the
+ * lambda planes (128-bit hash taken on the device) -- and whose cell rectangle lies inside the cached one (the table is
+ * built with a margin) skips the table pass: n_samples, the offsets (sigma) and the zoom are free to change.
+ * fg_stats.table_reused reports it.  Off by default (a batch render pays the 0.1 ms hash for nothing). */
+void fg_set_table_cache(fg_ctx* ctx, int enable);
+/* Progressive refinement: render samples [k_begin, k_end) of the n_samples offsets and merge them into the context's
+ * running image, so a preview can show N = 16 at once and refine to the full N without evaluating a sample twice.
+ * After the call `out` (and the context) hold the render of samples [0, k_end): bit-identical to fg_render_planes with
+ * n_samples = k_end and the first k_end offsets (sample counts are merged as integers).  k_begin = 0 starts a
+ * refinement; k_begin > 0 must equal the k_end of the previous fg_refine_planes call on this context with the same
+ * geometry, else FG_ERR_INVALID.  p->n_samples = the total N (its offsets size the cell table once for all slices).
+ * `cancel` as in fg_render_planes_cancelable (may be NULL).  Single frame, one device (a multi-device context uses
+ * its first device). */
+int fg_refine_planes(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, const float* const* lambda,
+                     const float* offsets, uint32_t k_begin, uint32_t k_end, float* const* out,
+                     const volatile int* cancel);
 
 /* ---- DEVICE-pointer variants (inputs already resident in HBM; asynchronous on the
  * context stream unless stream_sync != 0).  d_lambda / d_out hold n_planes planes

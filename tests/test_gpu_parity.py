@@ -424,6 +424,130 @@ def test_cancel_flag(ctx):
     ctx.render_pixelwise(fg_params_from(p, d), lam, off_in)
 
 
+@pytest.mark.parametrize("algo,path", [("pixel", 1), ("pixel", 3), ("grain", 0)], ids=["pixel-direct", "pixel-staged", "grain"])
+def test_cancel_flag_raised_mid_render_stops_the_launch(algo, path):
+    """The viewer's latest-job-wins worker (src/bin/viewer.rs:975-1028) cancels a render that is already running.  A
+    second thread raises the flag while the kernels execute: the call must return Cancelled well before an
+    uncancelled render of the same frame would have finished, and the context must render correctly afterwards."""
+    import threading
+    import time
+    import film_grain_b200 as fg
+    w, h = (3072, 2048) if path == 3 else (2048, 1024)
+    if algo == "pixel":
+        p = O.make_params(radius=0.1, n_samples=256 if path == 3 else 48, algo=O.ALGO_PIXEL)
+    else:
+        p = O.make_params(radius=0.5, n_samples=512, algo=O.ALGO_GRAIN)
+    d, off, off_in = O.derive_common(p, w, h)
+    lam = lambda_from_u8(noise_u8(w, h, seed=3)[:, :, 0], d.inv_e_pi_r2)
+    lams = [lam, lam, lam]
+    offs = off_in if algo == "pixel" else off
+    a = O.ALGO_PIXEL if algo == "pixel" else O.ALGO_GRAIN
+    q = fg_params_from(p, d, path=path)
+    with fg.Context(0) as c:
+        c.render_planes(q, a, lams, offs)  # warm-up: pools, attributes
+        flag = C.c_int(0)
+        c.set_cancel_flag(flag)            # armed but never raised: the kernels poll the device word, the result is unchanged
+        t0 = time.perf_counter()
+        full = c.render_planes(q, a, lams, offs)
+        t_full = time.perf_counter() - t0
+        assert t_full > 0.02, "the frame must be long enough to cancel"
+        for delay in (0.25, 0.5):
+            flag.value = 0
+            th = threading.Timer(delay * t_full, lambda: setattr(flag, "value", 1))
+            t0 = time.perf_counter()
+            th.start()
+            with pytest.raises(fg.Cancelled):
+                c.render_planes(q, a, lams, offs)
+            t_cancel = time.perf_counter() - t0
+            th.join()
+            assert t_cancel < delay * t_full + 0.35 * t_full + 0.01, (delay, t_cancel, t_full)
+        flag.value = 0
+        again = c.render_planes(q, a, lams, offs)  # the device word was lowered again
+        c.set_cancel_flag(None)
+        for k in range(3):
+            assert np.array_equal(again[k], full[k])
+    if algo == "pixel":  # a few rows of the cancelled-then-repeated frame against the oracle
+        ref = O.render_pixelwise(lam, p, d, off_in, y0=500, y1=504)
+        assert np.array_equal(again[0][500:504], ref[500:504])
+
+
+def test_table_cache_serves_renders_that_change_only_samples_sigma_and_zoom():
+    """fg_set_table_cache: N, the offsets (sigma) and the zoom do not enter the cell table, so the second and later renders
+    of a viewer session evaluate from the cached table (stats.table_reused) -- and must equal a from-scratch render and
+    the oracle bit for bit.  New content, a new seed or a rectangle the cached table does not cover rebuild it."""
+    import film_grain_b200 as fg
+    w, h = 160, 120
+    img = noise_u8(w, h, seed=41)
+    with fg.Context(0) as c, fg.Context(0) as fresh:
+        c.set_table_cache(True)
+        def render(ctxx, **kw):
+            p = O.make_params(algo=O.ALGO_PIXEL, **kw)
+            d, off, off_in = O.derive_common(p, w, h)
+            lams = [lambda_from_u8(img[:, :, k], d.inv_e_pi_r2) for k in range(3)]
+            out = ctxx.render_planes(fg_params_from(p, d, path=3), O.ALGO_PIXEL, lams, off_in)
+            return out, ctxx.stats().table_reused, (p, d, off_in, lams)
+        base = dict(radius=0.1, n_samples=16)
+        _, reused, _ = render(c, **base)
+        assert reused == 0
+        for kw, expect in [(dict(base, n_samples=64), 1),                       # more samples (same sigma: offsets are a prefix)
+                           (dict(base, n_samples=200), 1),                      # k_pixelwise_tri from the cached table
+                           (dict(base, n_samples=32, sigma_px=0.6), 1),         # smaller blur
+                           (dict(base, n_samples=32, zoom=1.5), 1),             # zoom in: a smaller cell rectangle
+                           (dict(base, n_samples=32, sigma_px=4.0), 0),         # much larger blur: outside the margin -> rebuild
+                           (dict(base, n_samples=32, sigma_px=3.0), 1),         # ... and the rebuilt (larger) table serves this
+                           (dict(base, n_samples=32, seed=77), 0),              # another realisation
+                           (dict(base, n_samples=32, seed=77, zoom=0.8), 1)]:
+            got, reused, (p, d, off_in, lams) = render(c, **kw)
+            assert reused == expect, (kw, reused)
+            ref, r0, _ = render(fresh, **kw)
+            assert r0 == 0
+            for k in range(3):
+                assert np.array_equal(got[k], ref[k]), kw
+            assert np.array_equal(got[1], O.render_pixelwise(lams[1], p, d, off_in)), kw
+        img[10:20, 10:20, 1] ^= 0x55  # new content in one plane: the hash changes
+        _, reused, _ = render(c, **base)
+        assert reused == 0
+        c.set_table_cache(False)
+        _, reused, _ = render(c, **base)
+        assert reused == 0
+
+
+@pytest.mark.parametrize("algo", ["pixel", "grain"])
+def test_progressive_refinement_equals_one_render(ctx, algo):
+    """fg_refine_planes: 16 -> 48 -> 200 samples through the same table; after every step the image equals a single render
+    of that many samples (the oracle's), bit for bit; a slice that does not continue the previous one is refused."""
+    import film_grain_b200 as fg
+    w, h, n = 90, 70, 200
+    kw = dict(radius=0.1) if algo == "pixel" else dict(radius=0.5)
+    a = O.ALGO_PIXEL if algo == "pixel" else O.ALGO_GRAIN
+    p = O.make_params(algo=a, n_samples=n, **kw)
+    d, off, off_in = O.derive_common(p, w, h)
+    offs = off_in if algo == "pixel" else off
+    img = noise_u8(w, h, seed=5)
+    lams = [lambda_from_u8(img[:, :, k], d.inv_e_pi_r2) for k in range(2)]
+    q = fg_params_from(p, d)
+    ctx.set_table_cache(True)
+    try:
+        outs = None
+        k0 = 0
+        for k1 in (16, 48, 200):
+            outs = ctx.refine_planes(q, a, lams, offs, k0, k1, outs)
+            if algo == "pixel" and k0 > 0:
+                assert ctx.stats().table_reused in (0, 1)
+            pk = O.make_params(algo=a, n_samples=k1, **kw)
+            dk, offk, offk_in = O.derive_common(pk, w, h)
+            o_k = offk_in if algo == "pixel" else offk
+            assert np.array_equal(o_k, offs[:k1]), "the offsets of a smaller N are a prefix of the larger N's"
+            for k in range(2):
+                ref = O.render_pixelwise(lams[k], pk, dk, offk_in) if algo == "pixel" else O.render_grainwise(lams[k], pk, dk, offk)
+                assert np.array_equal(outs[k], ref), (k1, k)
+            k0 = k1
+        with pytest.raises(fg.GpuError):
+            ctx.refine_planes(q, a, lams, offs, 48, 64, outs)  # the context's refinement stands at 200
+    finally:
+        ctx.set_table_cache(False)
+
+
 def test_full_size_config2_plane_properties(ctx):
     """BASELINE.json configs[1] at full size (3840x2160, r=0.1, N=256, one colour plane): the strip
     kernel against (a) the oracle on two 6-row bands, (b) the independent direct kernel on three
