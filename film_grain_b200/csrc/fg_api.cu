@@ -210,8 +210,9 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
         if ((rc = ensure(ctx, ctx->scan_tmp, tmp_bytes))) return rc;
         FG_CUDA(ctx, cub::DeviceScan::ExclusiveSum(ctx->scan_tmp.p, tmp_bytes, it, (uint64_t*)ctx->scan_out.p, npix_in, ctx->stream));
         k_total<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->counts.p, (const uint64_t*)ctx->scan_out.p, npix_in, d_total);
-        FG_CUDA(ctx, cudaMemcpyAsync(&total, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         FG_CUDA(ctx, wait_stream(ctx));
+        total = ctx->h_pin[0];
         ctx->stats.launches += 4;
         if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
         if (total >> 32) tiled = false; // the tile kernel indexes a tile's grains with 32 bits
@@ -247,7 +248,7 @@ int grainwise_device_plane(fg_ctx* ctx, const fg_params* p, const RenderConsts& 
         FG_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint64_t), ctx->stream));
     }
     if (!ev4) FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-    ctx->fb_count_host = 0; // fg_get_stats: strip_ms = rasterisation, table_ms = grain generation of the last plane
+    ctx->fb_count_host() = 0; // fg_get_stats: strip_ms = rasterisation, table_ms = grain generation of the last plane
     ctx->strip_launches = 1;
     ctx->fb_pending = true;
     if (tiled) {
@@ -731,6 +732,12 @@ int fg_context_create(fg_ctx** out, int device) {
         return FG_ERR_CUDA_STICKY;
     }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    if (cudaHostAlloc((void**)&ctx->h_pin, 16 * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        fg_context_destroy(ctx);
+        return FG_ERR_OOM;
+    }
+    std::memset(ctx->h_pin, 0, 16 * sizeof(uint64_t));
     // in-launch cancel (fg_ctx.cuh: wait_stream); without these the flag is still honoured between the stages
     if (cudaStreamCreateWithFlags(&ctx->abort_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventDisableTiming) != cudaSuccess ||
@@ -802,6 +809,7 @@ void fg_context_destroy(fg_ctx* ctx) {
         if (ctx->ev_wait) cudaEventDestroy(ctx->ev_wait);
         if (ctx->d_abort) cudaFree(ctx->d_abort);
         if (ctx->h_one) cudaFreeHost(ctx->h_one);
+        if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         cudaGetLastError();
     }
@@ -821,7 +829,7 @@ void fg_get_stats(const fg_ctx* ctx, fg_stats* out) {
     *out = ctx->stats;
     if (!ctx->subs.empty()) return; // aggregated over the devices by the render call
     if (ctx->fb_pending) { // meaningful once the stream is synchronised
-        out->tiles_fallback = ctx->fb_count_host;
+        out->tiles_fallback = ctx->fb_count_host();
         out->strip_launches = ctx->strip_launches;
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]) == cudaSuccess) out->strip_ms = ms;

@@ -60,7 +60,11 @@ struct fg_ctx {
     // pools
     DevBuf lambda, out, offsets, bits, counts, scan_out, scan_tmp, grains, misc, tiles, thr, bitmap, rowinfo, ptab, gtab, fbtotal, rgb_in, rgb_out, chroma, lut, gw_states, acc, part;
     bool tables_ready = false;
-    uint32_t fb_count_host = 0; // tiled path: fallback-list length of the last render (valid after a stream sync)
+    // Page-locked landing area of the small device->host reads (a copy into pageable memory would block the host inside
+    // cudaMemcpyAsync until the stream gets there, i.e. for the whole kernel in front of it -- no polling, no cancel):
+    // [0] table / grain total, [1] overflow flag, [2..3] plane hash, [4] fallback-list length of the last render
+    uint64_t* h_pin = nullptr;
+    uint32_t& fb_count_host() const { return *(uint32_t*)(h_pin + 4); } // valid after a stream sync
     bool fb_pending = false;
     size_t table_max = (size_t)48 << 30; // cell-table budget per band (FG_B200_TABLE_MAX_BYTES overrides; tests)
     double table_slack_sigma = 8.0; // row capacity = expected grains + this many sigma + 64 (FG_B200_TABLE_SLACK_SIGMA: tests)

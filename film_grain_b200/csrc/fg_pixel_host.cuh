@@ -302,6 +302,9 @@ TriPlan tri_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, i
         for (int n = 1; n <= max_n; ++n) best_eff = std::max(best_eff, seg_eff(n));
         for (int n = 1; n <= max_n; ++n)
             if (seg_eff(n) >= best_eff - 0.005) { best_n = n; break; } // among near-optimal splits the coarsest: fewer ramps
+        if (cancel_armed(ctx)) // a cancel flag is tested when a CTA starts: many short segments bound the latency of a cancel
+            for (int n = best_n; n <= max_n; ++n)
+                if (seg_eff(n) >= best_eff - 0.03) best_n = n;
         g.SEG = seg_of(best_n);
         static const int seg_forced = std::getenv("FG_B200_TRI_SEG") ? std::atoi(std::getenv("FG_B200_TRI_SEG")) : 0; // experiments
         if (seg_forced > 0) g.SEG = seg_forced;
@@ -390,12 +393,13 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         int rc0;
         if ((rc0 = ensure(ctx, ctx->misc, 64))) return rc0;
         unsigned long long* d_h = (unsigned long long*)ctx->misc.p + 2;
-        unsigned long long hh[2] = {0, 0};
         FG_CUDA(ctx, cudaMemsetAsync(d_h, 0, 16, ctx->stream));
         k_hash_planes<<<(unsigned)std::min<size_t>((n_in + 255) / 256, (size_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(d_lambda, n_in, d_h);
         FG_CUDA(ctx, cudaGetLastError());
-        FG_CUDA(ctx, cudaMemcpyAsync(hh, d_h, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        FG_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin + 2, d_h, 16, cudaMemcpyDeviceToHost, ctx->stream));
         FG_CUDA(ctx, wait_stream(ctx));
+        if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
+        const uint64_t hh[2] = {ctx->h_pin[2], ctx->h_pin[3]};
         ctx->stats.launches += 1;
         key.seed_cell = c.seed_cell; key.h0 = hh[0]; key.h1 = hh[1];
         key.seeding = c.seeding; key.in_w = p->in_w; key.in_h = p->in_h; key.n_planes = (uint32_t)n_planes; key.lognorm = c.rad.lognorm;
@@ -479,8 +483,9 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
             k_row_bases<<<1, 1024, 0, s>>>(d_S, g.bm_j0, g.bm_rows, n_planes, ctx->table_slack_sigma, d_rowbase, d_rowcap, c);
             FG_CUDA(ctx, cudaGetLastError());
             FG_CUDA(ctx, cudaMemsetAsync(d_overflow, 0, 4, s));
-            FG_CUDA(ctx, cudaMemcpyAsync(&total, d_rowbase + n_rows_all, 8, cudaMemcpyDeviceToHost, s));
+            FG_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin, d_rowbase + n_rows_all, 8, cudaMemcpyDeviceToHost, s));
             FG_CUDA(ctx, wait_stream(ctx));
+            total = ctx->h_pin[0];
             if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
         }
         const size_t bpg = c.rad.lognorm ? 14 : 10;
@@ -507,9 +512,9 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         else { if (joint) FG_LAUNCH_GEN(false, 3); else FG_LAUNCH_GEN(false, 1); }
 #undef FG_LAUNCH_GEN
         FG_CUDA(ctx, cudaGetLastError());
-        uint32_t overflow = 0;
-        FG_CUDA(ctx, cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, s));
+        FG_CUDA(ctx, cudaMemcpyAsync(ctx->h_pin + 1, d_overflow, 4, cudaMemcpyDeviceToHost, s));
         FG_CUDA(ctx, wait_stream(ctx));
+        const uint32_t overflow = *(const uint32_t*)(ctx->h_pin + 1);
         if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
         ctx->stats.launches += 3;
         if (overflow) return 3; // a row outgrew its expected size + 8 sigma (or a cell holds > 65535 grains): regenerate in-kernel instead
@@ -639,7 +644,7 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
         rc = FG_OK;
     }
     if (rc) return rc;
-    FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host, d_fbtotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    FG_CUDA(ctx, cudaMemcpyAsync(&ctx->fb_count_host(), d_fbtotal, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->fb_pending = true;
     return FG_OK;
 }

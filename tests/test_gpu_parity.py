@@ -451,16 +451,21 @@ def test_cancel_flag_raised_mid_render_stops_the_launch(algo, path):
         full = c.render_planes(q, a, lams, offs)
         t_full = time.perf_counter() - t0
         assert t_full > 0.02, "the frame must be long enough to cancel"
-        for delay in (0.25, 0.5):
+        for delay in (0.2, 0.45, 0.7):  # pixel-wise staged: table pass, evaluation kernel, late in the evaluation kernel
             flag.value = 0
-            th = threading.Timer(delay * t_full, lambda: setattr(flag, "value", 1))
-            t0 = time.perf_counter()
+            raised = [0.0]
+
+            def raise_flag():
+                raised[0] = time.perf_counter()
+                flag.value = 1
+            th = threading.Timer(delay * t_full, raise_flag)
             th.start()
             with pytest.raises(fg.Cancelled):
                 c.render_planes(q, a, lams, offs)
-            t_cancel = time.perf_counter() - t0
+            t_after = time.perf_counter() - raised[0]
             th.join()
-            assert t_cancel < delay * t_full + 0.35 * t_full + 0.01, (delay, t_cancel, t_full)
+            # one CTA lifetime + the drain of the launch, not the rest of the frame
+            assert t_after < max(0.2 * t_full, 0.008), (delay, t_after, t_full)
         flag.value = 0
         again = c.render_planes(q, a, lams, offs)  # the device word was lowered again
         c.set_cancel_flag(None)
