@@ -96,6 +96,11 @@ HOST_ABI = {
     "fgh_context": (_VP, [C.c_int]),
     "fgh_invalidate_context": (None, []),
     "fgh_logf_restated": (None, [_VP, C.c_uint64, _VP]),
+    "fgh_render_file": (C.c_int, [_P(FghParams), C.c_char_p, C.c_char_p, C.c_char_p, _P(C.c_uint32), C.c_int, C.c_int,
+                                  _P(C.c_int), _P(FghDerived)]),
+    "fgh_load_image": (C.c_int, [C.c_char_p, _P(_VP), _P(C.c_uint64), _P(C.c_uint64)]),
+    "fgh_free": (None, [_VP]),
+    "fgh_save_image": (C.c_int, [C.c_char_p, _VP, C.c_uint64, C.c_uint64, C.c_char_p]),
 }
 
 _lib = None

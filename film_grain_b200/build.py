@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libfg_b200.so")
-SOURCES = ["fg_api.cu", os.path.join("..", "host", "film_grain.cpp")]
+SOURCES = ["fg_api.cu", os.path.join("..", "host", "film_grain.cpp"), os.path.join("..", "host", "image_io.cpp")]
 
 
 def deps() -> list[str]:
@@ -43,6 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
            "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-ccbin", "/usr/bin/g++",
            "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-lz"]  # PNG (host/image_io.cpp)
     cmd += os.environ.get("FG_NVCC_EXTRA", "").split()  # experiments only (e.g. -DFG_TILE_WARPS=32)
     if verbose:
         cmd.insert(1, "-Xptxas")

@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import enum
+import os
 
 import numpy as np
 
@@ -195,3 +196,44 @@ def render_with_input_image(image_u8: np.ndarray, params: Params, fused: bool = 
     if rc != 0:
         raise RenderError(lib.fgh_last_error().decode())
     return out, d
+
+
+def _raise(rc: int):
+    lib = _lib.load()
+    if rc == -103:
+        raise Cancelled()
+    if rc == -102:
+        raise GpuError(-6, lib.fgh_last_error().decode())
+    if rc == -101:
+        raise ParamsError(lib.fgh_last_error().decode())
+    if rc != 0:
+        raise RenderError(lib.fgh_last_error().decode())
+
+
+def load_image(path: str) -> np.ndarray:
+    """image::open + to_rgb (src/color.rs:26-29): PNG / binary PNM -> u8 [H,W,3]."""
+    lib = _lib.load()
+    buf, w, h = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    _raise(lib.fgh_load_image(os.fsencode(path), C.byref(buf), C.byref(w), C.byref(h)))
+    try:
+        return np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_uint8)), (h.value, w.value, 3)).copy()
+    finally:
+        lib.fgh_free(buf)
+
+
+def save_image(path: str, image_u8: np.ndarray, fmt: str | None = None):
+    """save_with_format (src/lib.rs:65-68); the format comes from `fmt`, else the extension, else PNG."""
+    img = np.ascontiguousarray(image_u8, np.uint8)
+    h, w, _ = img.shape
+    _raise(_lib.load().fgh_save_image(os.fsencode(path), C.c_void_p(img.ctypes.data), w, h, fmt.encode() if fmt else None))
+
+
+def render(params: Params, input_path: str, output_path: str, output_format: str | None = None, roi=None,
+           fused: bool = False, device: int = 0, cancel=None):
+    """render(params) (src/lib.rs:57-71): image file in, image file out, on the device."""
+    info = FghDerived()
+    roi4 = (C.c_uint32 * 4)(*roi) if roi is not None else None
+    _raise(_lib.load().fgh_render_file(C.byref(params.builder._c()), os.fsencode(input_path), os.fsencode(output_path),
+                                       output_format.encode() if output_format else None, roi4, 1 if fused else 0, device,
+                                       C.byref(cancel) if cancel is not None else None, C.byref(info)))
+    return info

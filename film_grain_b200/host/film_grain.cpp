@@ -2,6 +2,7 @@
 // Compiled with -ffp-contract=off: every f32 expression keeps the reference's operand order and
 // is never fused, so Derived (delta, rm, inv_e_pi_r2, offsets) is bit-identical to the Rust host's.
 #include "film_grain.hpp"
+#include "image_io.hpp"
 
 #include <algorithm>
 #include <array>
@@ -647,6 +648,44 @@ fg_ctx* fgh_context(int device) {
 }
 
 void fgh_invalidate_context(void) { cuda::invalidate_context(); }
+
+int fgh_render_file(const fgh_params* p, const char* input_path, const char* output_path, const char* format_token,
+                    const uint32_t* roi4, int fused, int device, const volatile int* cancel, fgh_derived* info) {
+    return guarded([&] {
+        if (!p || !input_path || !output_path) throw RenderError(RenderError::Message, "NULL argument");
+        Params params = to_builder(p).build();
+        Roi roi{};
+        if (roi4) { // ensure_roi, src/params.rs:330-341
+            roi = Roi{roi4[0], roi4[1], roi4[2], roi4[3]};
+            if (roi.x1 <= roi.x0 || roi.y1 <= roi.y0) throw ParamsError("roi", "roi end must be greater than start (exclusive bounds)");
+        }
+        const RenderStats st = render_file(params, input_path, output_path, format_token, roi4 ? &roi : nullptr, fused != 0, cancel, device);
+        if (info) {
+            Derived d = derive_common(params, st.input_w, st.input_h);
+            fill_derived(params, d, info);
+        }
+    });
+}
+
+int fgh_load_image(const char* path, uint8_t** rgb, uint64_t* w, uint64_t* h) {
+    return guarded([&] {
+        if (!path || !rgb || !w || !h) throw RenderError(RenderError::Message, "NULL argument");
+        InputImage img = load_image(path);
+        uint8_t* buf = (uint8_t*)std::malloc(img.rgb.size() ? img.rgb.size() : 1);
+        if (!buf) throw RenderError(RenderError::Message, "out of host memory");
+        std::memcpy(buf, img.rgb.data(), img.rgb.size());
+        *rgb = buf; *w = img.width; *h = img.height;
+    });
+}
+
+void fgh_free(void* p) { std::free(p); }
+
+int fgh_save_image(const char* path, const uint8_t* rgb, uint64_t w, uint64_t h, const char* format_token) {
+    return guarded([&] {
+        if (!path || !rgb) throw RenderError(RenderError::Message, "NULL argument");
+        save_image(path, rgb, w, h, resolve_format(path, format_token));
+    });
+}
 
 void fgh_logf_restated(const float* x, uint64_t n, float* out) {
     for (uint64_t k = 0; k < n; ++k) out[k] = fg::logf_libm(x[k]);

@@ -11,6 +11,8 @@
  *   fgh_render_with_input_image    <- render_with_input_image(_cancelable) with Device::Gpu
  *                                     src/lib.rs:78-93, 134-173
  *   fgh_context / fgh_invalidate_context <- wgpu::context / invalidate_context src/wgpu/mod.rs:84-92
+ *   fgh_render_file / fgh_load_image / fgh_save_image <- render(params), image::open, save_with_format
+ *                                     src/lib.rs:57-71, src/color.rs:26-29
  */
 #ifndef FG_HOST_H
 #define FG_HOST_H
@@ -68,6 +70,21 @@ int fgh_render_with_input_image(const fgh_params* p, const uint8_t* rgb, uint64_
  * (a context handed out here is not destroyed by fgh_invalidate_context or by a device switch). */
 fg_ctx* fgh_context(int device);
 void fgh_invalidate_context(void);
+/* ---- image files ----------------------------------------------------------------------------------
+ * fgh_render_file <- render(params) src/lib.rs:57-71: image::open (src/color.rs:26-29), ROI crop (src/color.rs:215-231),
+ * render on the device, fs::create_dir_all of the output's parent, save_with_format with the format resolved from
+ * `format_token` or the output extension, PNG when there is none (src/lib.rs:188-203).  This build reads and writes PNG
+ * (8-bit and 1/2/4-bit grey / palette, non-interlaced; alpha dropped like to_rgb32f) and binary PNM (P5 / P6, maxval
+ * 255); other known formats -> FGH_ERR_MESSAGE "not built into this engine", unknown tokens -> the reference's message.
+ * roi4 = {x0, y0, x1, y1} (exclusive end) or NULL. */
+int fgh_render_file(const fgh_params* p, const char* input_path, const char* output_path, const char* format_token,
+                    const uint32_t* roi4, int fused, int device, const volatile int* cancel, fgh_derived* info);
+/* image::open -> 8-bit interleaved RGB in a malloc'ed buffer (release with fgh_free). */
+int fgh_load_image(const char* path, uint8_t** rgb, uint64_t* w, uint64_t* h);
+void fgh_free(void* p);
+/* save_with_format: format from `format_token`, else from the extension of `path`, else PNG. */
+int fgh_save_image(const char* path, const uint8_t* rgb, uint64_t w, uint64_t h, const char* format_token);
+
 /* The libm logf restatement the fused luma path runs on the device (csrc/fg_logf.h), host build:
  * lets the CPU tests compare it with the platform's logf. */
 void fgh_logf_restated(const float* x, uint64_t n, float* out);
