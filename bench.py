@@ -64,14 +64,54 @@ def synth_image(kind: str, w: int, h: int) -> np.ndarray:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region (B200_PROFILING.md).  NVML in a thread
+    of this process, one sample every 10 ms (a `nvidia-smi -lms` child can take longer to print its first row than
+    the whole timed region lasts); `nvidia-smi` is the fallback when the NVML binding is missing."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
         self.index = index
-        self.rows: list[list[str]] = []
+        self.rows: list[tuple] = []      # (sm MHz, max MHz, reason names)
         self.proc = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.source = None
+
+    def _nvml_loop(self, nv, h):
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self.rows.append((sm, mx, tuple(n for b, n in self.REASONS if bits & b)))
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:  # NVML enumerates every GPU of the box, CUDA only the visible ones
+                ids = [t.strip() for t in vis.split(",") if t.strip()]
+                if self.index < len(ids) and ids[self.index].isdigit():
+                    idx = int(ids[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.source = "nvml"
+            self._thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -79,36 +119,41 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 7:
-                self.rows.append(parts)
+                try:
+                    self.rows.append((float(parts[0]), float(parts[1]),
+                                      tuple(n for n, v in zip(names, parts[3:7]) if v.lower().startswith("active"))))
+                except ValueError:
+                    continue
 
     def stop(self) -> dict:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1)
         if self.proc is not None:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        busy = [s for s in sm if s > 0]
+        rows = list(self.rows)
+        sm = [r[0] for r in rows]
+        mx = [r[1] for r in rows if r[1] is not None]
+        reasons = set()
+        for r in rows:
+            reasons.update(r[2])
+        busy = [v for v in sm if v > 0]
         return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def oracle_sample(wl: dict, img: np.ndarray, seconds: float, nthreads: int = 0):

@@ -119,6 +119,10 @@ struct StageGeo {
     uint32_t ppitch;          // Pg entries per row (>= cols + 1, multiple of 8)
 };
 
+// The general sampler as a real call: inlined three times (once per plane) it set the register count of the whole kernel,
+// i.e. the occupancy of the hot Knuth path, although only saturated content ever runs it.
+__device__ __noinline__ uint32_t poisson_f64_counted(XoshiroCounted& r, double lambda) { return poisson_f64(r, lambda); }
+
 // One WARP per cell row, no CTA-wide barriers.  NPL = 3: the warp generates the row for all three colour planes
 // together; NPL = 1: one warp per (plane, row), any plane count.  A cell is seeded from (seed, i, j) only
 // (src/rng.rs:26-29), and its Knuth chain p_k = U1 ... Uk is the same sequence for every plane -- a plane only decides
@@ -135,11 +139,19 @@ struct StageGeo {
 // planes needs the general sampler (lambda' >= 12, e < 0) parks all its planes from the seed state instead, with the
 // sampler's own draw count as the skip.  A final scan over the tile's counts writes the prefix entries of ALL its cells.
 #define FG_GW_WARPS 4
+// Tile size and resident CTAs per SM, measured at C2 (table pass, ms; joint instance): 1024 / unconstrained (130
+// registers, 3 CTAs) 21.1; 1024 / 4 CTAs 19.2; 512 / 4 19.1; 512 / 5 (96 registers) 18.8; 768 / 5 18.4; 768 / 6 (80
+// registers, spills) 19.3; 512 / 7 19.9; 256 / 7 21.0.  Per-plane instance: unconstrained 20.8, 5 CTAs 19.7, 6 19.3,
+// 7 19.9, 8 21.1.  The kernel is latency-bound (55% issue-active at 12 warps per SM), so one more resident CTA pays
+// for a few spills -- until the spills reach the chain loop.
 #ifndef FG_GW_TILE
-#define FG_GW_TILE 1024 // cells per tile: a multiple of 256 (phase c: FG_GW_TILE / 32 cells per lane, 8 per store pair)
+#define FG_GW_TILE 768 // cells per tile: a multiple of 256 (phase c: FG_GW_TILE / 32 cells per lane, 8 per store pair)
 #endif
 #ifndef FG_GW_MINB
-#define FG_GW_MINB 1
+#define FG_GW_MINB 5
+#endif
+#ifndef FG_GW_MINB1
+#define FG_GW_MINB1 6 // the per-plane instance needs fewer registers
 #endif
 #define FG_GW_QCAP 64
 template <int NPL>
@@ -153,7 +165,7 @@ struct GenWarpSmem {
 };
 
 template <bool LOGN, int NPL>
-__global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
+__global__ void __launch_bounds__(FG_GW_WARPS * 32, NPL == 1 ? FG_GW_MINB1 : FG_GW_MINB) k_gen_rows(const uint32_t* __restrict__ bm_planes, size_t bm_plane_words,
                                                                 const double* __restrict__ e_planes, const float* __restrict__ lambda,
                                                                 size_t in_stride, uint32_t* __restrict__ Pg,
                                                                 const uint64_t* __restrict__ rowbase, const uint32_t* __restrict__ rowcap,
@@ -169,23 +181,17 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
     const int j = geo.j0 + row;
     const float sy = __fmul_rn(__int2float_rn(j), c.delta);
     const int iy = min(max(floor_i32(sy), 0), c.in_h - 1);
-    const double* erow[NPL];
-    const float* lrow[NPL];
-    const uint32_t* bmrow[NPL];
-    uint64_t base[NPL];
-    uint32_t cap[NPL], run[NPL]; // run: grains of the row placed so far
-    uint32_t* prow[NPL];
+    // per-plane addresses are the first plane's plus a plane stride (registers: 130 -> fewer, one more resident CTA);
+    // the row's base and capacity are read from the (L1-resident) row arrays where they are needed
+    const double* const erow0 = e_planes + in_stride * plane0 + (size_t)iy * c.in_w;
+    const float* const lrow0 = lambda + in_stride * plane0 + (size_t)iy * c.in_w;
+    const uint32_t* const bmrow0 = bm_planes + bm_plane_words * plane0 + (size_t)row * geo.pitchw;
+    const size_t ridx0 = (size_t)plane0 * geo.rows + row;
+    uint32_t* const prow0 = Pg + ridx0 * geo.ppitch;
+    const size_t pstride = (size_t)geo.rows * geo.ppitch; // Pg entries between the same row of two planes
+    uint32_t run[NPL]; // grains of the row placed so far
 #pragma unroll
-    for (int pl = 0; pl < NPL; ++pl) {
-        const size_t ridx = (size_t)(plane0 + pl) * geo.rows + row;
-        erow[pl] = e_planes + in_stride * (plane0 + pl) + (size_t)iy * c.in_w;
-        lrow[pl] = lambda + in_stride * (plane0 + pl) + (size_t)iy * c.in_w;
-        bmrow[pl] = bm_planes + bm_plane_words * (plane0 + pl) + (size_t)row * geo.pitchw;
-        base[pl] = rowbase[ridx];
-        cap[pl] = rowcap[ridx];
-        prow[pl] = Pg + ridx * geo.ppitch;
-        run[pl] = 0;
-    }
+    for (int pl = 0; pl < NPL; ++pl) run[pl] = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t qn = 0;  // parked (cell, plane) pairs
 
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
         uint32_t bits = 0u;
         if (lane < FG_GW_TILE / 32 && widx < geo.pitchw) {
 #pragma unroll
-            for (int pl = 0; pl < NPL; ++pl) bits |= __ldg(bmrow[pl] + widx);
+            for (int pl = 0; pl < NPL; ++pl) bits |= __ldg(bmrow0 + bm_plane_words * pl + widx);
         }
         const uint32_t nb = __popc(bits);
         const uint32_t inclA = warp_incl(nb);
@@ -298,7 +304,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
                 double e[NPL];
 #pragma unroll
                 for (int pl = 0; pl < NPL; ++pl) {
-                    e[pl] = __ldg(erow[pl] + ix);
+                    e[pl] = __ldg(erow0 + in_stride * pl + ix);
                     genlane |= e[pl] < 0.0;
                 }
                 Xoshiro rng;
@@ -310,8 +316,8 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
                         XoshiroCounted rc;
                         rc.s0 = rng.s0; rc.s1 = rng.s1; rc.s2 = rng.s2; rc.s3 = rng.s3; rc.n = 0;
                         if (e[pl] < 0.0) {
-                            const float lam = __ldg(lrow[pl] + ix);
-                            q[pl] = poisson_f64(rc, (double)__fmul_rn(__fmul_rn(lam, c.delta), c.delta));
+                            const float lam = __ldg(lrow0 + in_stride * pl + ix);
+                            q[pl] = poisson_f64_counted(rc, (double)__fmul_rn(__fmul_rn(lam, c.delta), c.delta));
                         } else {
                             double p = standard_f64(rc);
                             while (p > e[pl]) { p = __dmul_rn(p, standard_f64(rc)); ++q[pl]; }
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
             }
             bool over = false;
 #pragma unroll
-            for (int pl = 0; pl < NPL; ++pl) over |= (uint64_t)run[pl] + total[pl] > cap[pl];
+            for (int pl = 0; pl < NPL; ++pl) over |= (uint64_t)run[pl] + total[pl] > __ldg(rowcap + ridx0 + (size_t)geo.rows * pl);
             if (over) { // uniform
                 if (lane == 0) atomicExch(overflow, 1u);
                 return;
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
             uint32_t one = 0; // planes whose cell holds exactly one grain: its position is drawn once, here
 #pragma unroll
             for (int pl = 0; pl < NPL; ++pl) {
-                dst[pl] = base[pl] + run[pl] + excl[pl];
+                dst[pl] = __ldg(rowbase + ridx0 + (size_t)geo.rows * pl) + run[pl] + excl[pl];
                 if (q[pl]) sm.cnt[pl][cl] = (uint16_t)q[pl];
                 if (q[pl] == 1u && !genlane) one |= 1u << pl;
                 run[pl] += total[pl];
@@ -449,7 +455,7 @@ __global__ void __launch_bounds__(FG_GW_WARPS * 32, FG_GW_MINB) k_gen_rows(const
                 o1.z = pacc; pacc += w[3] & 0xFFFFu;
                 o1.w = pacc; pacc += w[3] >> 16;
                 if (k0 + 8 * k < (int)geo.ppitch) { // ppitch is a multiple of 8
-                    uint4* dstp = (uint4*)(prow[pl] + k0 + 8 * k);
+                    uint4* dstp = (uint4*)(prow0 + pstride * pl + k0 + 8 * k);
                     dstp[0] = o0;
                     dstp[1] = o1;
                 }
