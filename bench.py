@@ -393,6 +393,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits that must not put a spinning kernel on a GPU
     dev = torch.device("cuda", local_rank)
 
     prep = Prepared(args.workload)
@@ -619,7 +620,8 @@ def main():
     # as the reference's render() gets from the box.  Rank 0 drives all N GPUs (one host thread + stream per device inside the
     # library); the other ranks wait at a barrier.  Pinned host planes in and out, copies inside the timed region.
     if world > 1:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=cpu_group)  # gloo: the waiting ranks leave their GPUs idle (an NCCL barrier spins ON the GPU rank 0 is about to use from this process, and the two processes would time-slice it)
         if rank == 0:
             try:
                 mctx = fg.Context(devices=list(range(world)))
@@ -645,7 +647,7 @@ def main():
                 mctx.close()
             except Exception as e:  # a side measurement never costs the headline line
                 e2e["single_process"] = {"error": repr(e)[:300]}
-        dist.barrier()
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
