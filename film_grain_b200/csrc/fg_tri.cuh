@@ -374,7 +374,15 @@ k_pixelwise_tri(const float* __restrict__ lambda, size_t in_stride, const float2
                         hb = HB + ((uint32_t)(y - Y0) & (uint32_t)(cfg.RH - 1)) * HBROW + (uint32_t)(warp * SPW + is) * 4u;
                         const bool fast = j1 - j0 == 2 && j0 >= Jb && j0 < Jb + D && j0 >= cfg.bm_j0 && (long long)j0 + 2 < (long long)cfg.bm_j0 + cfg.bm_rows;
                         if (fast) { w3 = (uint32_t)(j0 - Jbase); qa = Qs + (w3 % (uint32_t)NQ) * PSB; } // w3: the row, should its group turn out skipped
-                        else if (j0 <= j1) slow = true;
+                        else if (j0 <= j1) {
+                            slow = true;
+                            // FOUR cell rows: from y = 2048 / zoom on, the f32 rounding of (yg -/+ rm) / delta makes 0.4% of the
+                            // (row, sample) items span j0 .. j0 + 3 -- and 99% of the output rows hold such an item.  Rows
+                            // j0 .. j0 + 3 are exactly the union of the merged triples j0 and j0 + 1, both in this step's
+                            // window: the item is served from shared memory (bit 31 of w3), not by a walk of the HBM table.
+                            if (j1 - j0 == 3 && j0 >= Jb && j0 + 1 < Jb + D && j0 >= cfg.bm_j0 && (long long)j0 + 3 < (long long)cfg.bm_j0 + cfg.bm_rows)
+                                w3 = (uint32_t)(j0 - Jbase) | 0x80000000u;
+                        }
                     }
                 }
                 __syncwarp();
@@ -406,6 +414,25 @@ k_pixelwise_tri(const float* __restrict__ lambda, size_t in_stride, const float2
                 sb &= sb - 1;
                 const uint4 it = tri_lds_v4(ibase + (uint32_t)L * 16u);
                 const float ygs = __uint_as_float(it.z);
+                if ((it.w & 0x80000000u) && !state[4 + (tau & 1)]) { // four rows = two merged triples of the window (all rows merged)
+                    const int ssel = L % SPW;
+                    uint32_t ab = 0u;
+                    float xg = 0.0f;
+#pragma unroll
+                    for (int s = 0; s < SPW; ++s)
+                        if (s == ssel) { ab = ab_r[s]; xg = xg_r[s]; }
+                    const uint64_t pp = pack_f32x2(ygs, xg);
+                    const uint32_t wrow = it.w & 0x7FFFFFFFu;
+                    bool hit4 = false;
+#pragma unroll
+                    for (uint32_t t = 0; t < 2u; ++t) {
+                        const uint32_t qa4 = Qs + ((wrow + t) % (uint32_t)NQ) * PSB;
+                        const uint32_t s16 = tri_lds_u16(qa4 + (ab & 0xFFFFu)), e16 = tri_lds_u16(qa4 + (ab >> 16));
+                        for (uint32_t g = s16; g < e16 && !hit4; ++g) hit4 = dist2_packed(pp, lds_f32x2(Ms + g * 8u)) <= r2;
+                    }
+                    tri_sts_u32(it.y, __ballot_sync(0xFFFFFFFFu, hit4));
+                    continue;
+                }
                 const int sj0 = cell_lo(ygs, rm, delta), sj1 = cell_hi(ygs, rm, delta);
                 if (sj0 < cfg.bm_j0 || (long long)sj1 >= (long long)cfg.bm_j0 + cfg.bm_rows) {
                     if (lane == 0 && atomicExch((uint32_t*)&state[1], 1u) == 0u) push_fallback(fb_list, fb_count, fb_cap, X0, Y0, X1 - X0 + 1, Y1 - Y0, plane);

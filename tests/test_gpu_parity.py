@@ -153,6 +153,25 @@ def test_tri_kernel_matches_oracle(ctx, monkeypatch, name, w, h, kw, content):
     assert np.array_equal(band[r0:r1], ref[r0:r1])
 
 
+def test_tri_kernel_rows_beyond_2048_visit_four_cell_rows(ctx):
+    """From y = 2048 input pixels on, the f32 rounding of (yg -/+ rm) / delta makes some (row, sample) items span FOUR cell
+    rows (never below: the oracle's own arithmetic, counted here).  k_pixelwise_tri serves them from two merged triples
+    in shared memory; the band across the 2048 boundary must equal the oracle bit for bit."""
+    w, h, n = 40, 2200, 160
+    p = O.make_params(radius=0.1, n_samples=n, algo=O.ALGO_PIXEL)
+    d, off, off_in = O.derive_common(p, w, h)
+    rm, dl = np.float32(d.rm), np.float32(d.delta)
+    yy = (np.arange(2030, 2200, dtype=np.float32)[:, None] + np.float32(0.5)) - off_in[:, 1][None, :].astype(np.float32)
+    span = np.floor(((yy + rm).astype(np.float32) / dl).astype(np.float32)) - np.floor(((yy - rm).astype(np.float32) / dl).astype(np.float32))
+    assert (span[:18] == 2).all() and (span[18:] == 3).any(), "the premise: four-row items exist from row 2048 on only"
+    lam = lambda_from_u8(noise_u8(w, h, seed=8)[:, :, 0], d.inv_e_pi_r2)
+    r0, r1 = 2030, 2200
+    ref = O.render_pixelwise(lam, p, d, off_in, y0=r0, y1=r1)
+    got = ctx.render_pixelwise(fg_params_from(p, d, path=3, rows=(r0, r1)), lam, off_in)
+    assert ctx.eval_kernel_name() == "k_pixelwise_tri"
+    assert np.array_equal(got[r0:r1], ref[r0:r1]), f"{np.count_nonzero(got[r0:r1] != ref[r0:r1])} px differ"
+
+
 @pytest.mark.parametrize("path", [2, 3], ids=["tiled", "staged"])
 def test_tiled_path_is_taken_and_fallback_is_exact(ctx, path):
     """The strip kernel serves ordinary content itself; saturated content (u8 255 -> 4.4 grains per

@@ -9,6 +9,7 @@ from film_grain_b200 import host as H
 from tests.helpers import noise_u8
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+which = int(sys.argv[2]) if len(sys.argv) > 2 else 3  # which of the n bands
 w, h, N = 3840, 2160, 256
 img = noise_u8(w, h)
 p = H.ParamsBuilder(radius_mean=0.1, n_samples=N, algo=H.Algo.Pixel, seed=5489, color_mode=H.ColorMode.Rgb).build()
@@ -21,8 +22,10 @@ d_out = torch.zeros((3, h, w), dtype=torch.float32, device=dev)
 rows = h // n
 with fg.Context(0) as ctx:
     blk = d.block
-    blk.row_begin, blk.row_end = 3 * rows, 4 * rows
+    blk.row_begin, blk.row_end = which * rows, (which + 1) * rows
+    if os.environ.get("ROWS"):  # explicit band: ROWS=r0:r1
+        blk.row_begin, blk.row_end = [int(v) for v in os.environ["ROWS"].split(":")]
     for i in range(6):
         ctx.render_planes_device(blk, fg.FG_ALGO_PIXEL, 3, d_lam.data_ptr(), d_off.data_ptr(), d_out.data_ptr(), sync=True)
         st = ctx.stats()
-        print(f"band 1/{n}: kernel {st.kernel_ms:.3f} ms  strip {st.strip_ms:.3f}  table {st.table_ms:.3f}  launches {st.launches}")
+        print(f"rows {blk.row_begin}:{blk.row_end} kernel {st.kernel_ms:.3f} ms  strip {st.strip_ms:.3f}  table {st.table_ms:.3f}  launches {st.launches}")
