@@ -194,43 +194,83 @@ __device__ __forceinline__ void tri_group<1>(uint32_t ia, const float* xg, const
     asm(FG_TRI_ASM(1) : "+r"(hits), "+r"(rem) : "r"(t0.n), "r"(t0.ga), "l"(t0.pp), "f"(r2), "r"(zinf));
 }
 
-// G samples of one (step, row): tests, the deferred walk of what is left, coverage words
-template <int G>
-__device__ __forceinline__ void tri_eval_group(uint32_t ia, const float* xg, const uint32_t* ab, uint32_t Ms, float r2, uint32_t zinf) {
-    uint32_t rem = 0u, hits = 0u; // per lane: bit s = sample s has more candidates / is covered
-    tri_group<G>(ia, xg, ab, Ms, r2, zinf, hits, rem);
-    // the lanes that are not covered after FG_TRI_U candidates and have more: early-exit walk of the rest
-    if (__any_sync(0xFFFFFFFFu, rem != 0u)) {
+// What a lane needs to re-derive the (column, sample) data of a sample chosen at run time (the remainder walk below):
+// registers cannot be indexed dynamically, so the abscissa and the packed column range are recomputed from the offset.
+struct TriLane {
+    const float2* offsets;
+    float bx, rm, delta;
+    int i_loA, NE, warp;
+};
+
+#ifndef FG_TRI_REM_ROW
+#define FG_TRI_REM_ROW 0 // 1: one remainder pass per (step, row), lanes walk different samples in parallel; 0: per group of samples
+#endif
+
+// G samples of one (step, row): the straight-line tests; hits / rem are accumulated at bit S0 + s
+template <int SPW, int S0>
+struct TriRow {
+    static __device__ __forceinline__ void run(uint32_t ia, const float* xg, const uint32_t* ab, uint32_t Ms, float r2, uint32_t zinf,
+                                               uint32_t& hitsAll, uint32_t& remAll) {
+        constexpr int G = SPW - S0 < FG_TRI_GSZ ? SPW - S0 : FG_TRI_GSZ;
+        uint32_t rem = 0u, hits = 0u; // per lane: bit s = sample s has more candidates / is covered
+        tri_group<G>(ia + (uint32_t)S0 * 16u, xg + S0, ab + S0, Ms, r2, zinf, hits, rem);
+#if !FG_TRI_REM_ROW
+        // the lanes that are not covered after FG_TRI_U candidates and have more: early-exit walk of the rest
+        if (__any_sync(0xFFFFFFFFu, rem != 0u)) {
 #pragma unroll
-        for (int s = 0; s < G; ++s) {
-            if ((rem >> s) & 1u) {
-                const uint4 it = tri_lds_v4(ia + (uint32_t)s * 16u);
-                const uint32_t s16 = tri_lds_u16(it.x + (ab[s] & 0xFFFFu)), e16 = tri_lds_u16(it.x + (ab[s] >> 16));
-                const uint32_t ga = Ms + s16 * 8u;
-                const uint64_t pp = pack_f32x2(__uint_as_float(it.z), xg[s]);
-                for (uint32_t uu = (uint32_t)FG_TRI_U; uu < e16 - s16; ++uu) {
-                    if (dist2_packed(pp, lds_f32x2(ga + uu * 8u)) <= r2) { hits |= 1u << s; break; }
+            for (int s = 0; s < G; ++s) {
+                if ((rem >> s) & 1u) {
+                    const uint4 it = tri_lds_v4(ia + (uint32_t)(S0 + s) * 16u);
+                    const uint32_t s16 = tri_lds_u16(it.x + (ab[S0 + s] & 0xFFFFu)), e16 = tri_lds_u16(it.x + (ab[S0 + s] >> 16));
+                    const uint32_t ga = Ms + s16 * 8u;
+                    const uint64_t pp = pack_f32x2(__uint_as_float(it.z), xg[S0 + s]);
+                    for (uint32_t uu = (uint32_t)FG_TRI_U; uu < e16 - s16; ++uu) {
+                        if (dist2_packed(pp, lds_f32x2(ga + uu * 8u)) <= r2) { hits |= 1u << s; break; }
+                    }
                 }
+            }
+            __syncwarp();
+        }
+        rem = 0u;
+#endif
+        hitsAll |= hits << S0;
+        remAll |= rem << S0;
+        TriRow<SPW, S0 + G>::run(ia, xg, ab, Ms, r2, zinf, hitsAll, remAll);
+    }
+};
+template <int SPW>
+struct TriRow<SPW, SPW> {
+    static __device__ __forceinline__ void run(uint32_t, const float*, const uint32_t*, uint32_t, float, uint32_t, uint32_t&, uint32_t&) {}
+};
+
+// The SPW samples of one (step, row): tests in groups of FG_TRI_GSZ, then ONE walk of what is left -- the lanes that are
+// not covered after FG_TRI_U candidates of a sample and have more (a few per thousand (lane, sample) pairs, but some
+// lane of a warp in most rows).  Every lane walks its own samples in the same loop, so two lanes with work in different
+// samples advance together instead of one group after the other.  Then the coverage words.
+template <int SPW>
+__device__ __forceinline__ void tri_eval_row(uint32_t ia, const float* xg, const uint32_t* ab, uint32_t Ms, float r2, uint32_t zinf,
+                                             const TriLane& L) {
+    uint32_t hits = 0u, rem = 0u;
+    TriRow<SPW, 0>::run(ia, xg, ab, Ms, r2, zinf, hits, rem);
+    if (__any_sync(0xFFFFFFFFu, rem != 0u)) {
+        while (rem) {
+            const int s = __ffs(rem) - 1;
+            rem &= rem - 1u;
+            const float xgs = __fsub_rn(L.bx, __ldg(L.offsets + (s * L.NE + L.warp)).x); // as in the set-up of xg_r / ab_r
+            const uint32_t abs_ = col_range_packed(xgs, L.rm, L.delta, L.i_loA);
+            const uint4 it = tri_lds_v4(ia + (uint32_t)s * 16u);
+            const uint32_t s16 = tri_lds_u16(it.x + (abs_ & 0xFFFFu)), e16 = tri_lds_u16(it.x + (abs_ >> 16));
+            const uint32_t ga = Ms + s16 * 8u;
+            const uint64_t pp = pack_f32x2(__uint_as_float(it.z), xgs);
+            for (uint32_t uu = (uint32_t)FG_TRI_U; uu < e16 - s16; ++uu) {
+                if (dist2_packed(pp, lds_f32x2(ga + uu * 8u)) <= r2) { hits |= 1u << s; break; }
             }
         }
         __syncwarp();
     }
 #pragma unroll
-    for (int s = 0; s < G; ++s) tri_sts_u32(tri_lds_u32(ia + (uint32_t)s * 16u + 4u), __ballot_sync(0xFFFFFFFFu, (hits >> s) & 1u));
+    for (int s = 0; s < SPW; ++s) tri_sts_u32(tri_lds_u32(ia + (uint32_t)s * 16u + 4u), __ballot_sync(0xFFFFFFFFu, (hits >> s) & 1u));
 }
-// the SPW samples of one (step, row) in groups of FG_TRI_GSZ
-template <int SPW, int S0>
-struct TriRow {
-    static __device__ __forceinline__ void run(uint32_t ia, const float* xg, const uint32_t* ab, uint32_t Ms, float r2, uint32_t zinf) {
-        constexpr int G = SPW - S0 < FG_TRI_GSZ ? SPW - S0 : FG_TRI_GSZ;
-        tri_eval_group<G>(ia + (uint32_t)S0 * 16u, xg + S0, ab + S0, Ms, r2, zinf);
-        TriRow<SPW, S0 + G>::run(ia, xg, ab, Ms, r2, zinf);
-    }
-};
-template <int SPW>
-struct TriRow<SPW, SPW> {
-    static __device__ __forceinline__ void run(uint32_t, const float*, const uint32_t*, uint32_t, float, uint32_t) {}
-};
 
 template <int SPW>
 __global__ void __launch_bounds__(FG_TRI_THREADS, 1)
@@ -349,6 +389,7 @@ k_pixelwise_tri(const float* __restrict__ lambda, size_t in_stride, const float2
             xg_r[s] = xg;
             ab_r[s] = ab;
         }
+        const TriLane tl{offsets_input, bx, rm, delta, i_loA, NE, warp};
         const int ipl = m * SPW; // items (row, sample) of one step
         uint32_t slowmask = 0u;  // items of the current batch that need the general evaluation
         int bstep = 0;           // position of the step in its item batch
@@ -404,7 +445,7 @@ k_pixelwise_tri(const float* __restrict__ lambda, size_t in_stride, const float2
                 slowmask |= __ballot_sync(0xFFFFFFFFu, conv) << (bstep * ipl);
                 __syncwarp();
             }
-            for (int r = 0; r < m; ++r) TriRow<SPW, 0>::run(ibase + (uint32_t)(r * SPW) * 16u, xg_r, ab_r, Ms, r2, ZINF);
+            for (int r = 0; r < m; ++r) tri_eval_row<SPW>(ibase + (uint32_t)(r * SPW) * 16u, xg_r, ab_r, Ms, r2, ZINF, tl);
             // ---- the rare items that do not visit exactly three cell rows or start outside the window: walk their cells in
             //      the HBM table, like k_pixelwise_table_tiles.  Cells outside the table cannot occur for planned geometry;
             //      if they do, the segment is handed to the fallback kernel, which overwrites it. ----
