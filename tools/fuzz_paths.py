@@ -34,7 +34,7 @@ def main():
         elif kind == 3:
             img[:, :] = int(rng.integers(0, 256))
         radius = float(rng.choice([0.05, 0.07, 0.1, 0.12, 0.15, 0.2, 0.3, 0.5, 0.8, 1.3]))
-        kw = dict(radius=radius, n_samples=int(rng.choice([1, 2, 5, 16, 33, 64, 100, 130, 257])),
+        kw = dict(radius=radius, n_samples=int(rng.choice([1, 2, 5, 16, 33, 64, 100, 130, 200, 257])),
                   zoom=float(rng.choice([0.6, 1.0, 1.0, 1.0, 1.5, 2.0, 3.0])), seed=int(rng.integers(0, 2**32)))
         if rng.random() < 0.3:
             kw.update(radius_dist=O.DIST_LOGNORM, radius_stddev=radius * float(rng.choice([0.2, 0.5])))
@@ -61,6 +61,16 @@ def main():
                     if not (np.array_equal(got, ref) and np.array_equal(band, ref)):
                         bad += 1
                         print("MISMATCH pixel path", path, w, h, kw, (a, b), flush=True)
+                if rng.random() < 0.5:  # three planes at once: the joint table generation (k_gen_rows<., 3>), each plane against the oracle
+                    img2 = rng.integers(0, 256, (h, w), dtype=np.uint8)
+                    if rng.random() < 0.3:
+                        img2[: h // 2] = 255
+                    lam2 = lambda_from_u8(img2, d.inv_e_pi_r2)
+                    ref2 = O.render_pixelwise(lam2, p, d, off_in)
+                    outs = ctx.render_planes(fg_params_from(p, d, path=3), O.ALGO_PIXEL, [lam, lam2, lam], off_in)
+                    if not (np.array_equal(outs[0], ref) and np.array_equal(outs[1], ref2) and np.array_equal(outs[2], ref)):
+                        bad += 1
+                        print("MISMATCH pixel 3-plane", w, h, kw, flush=True)
             else:
                 ref = O.render_grainwise(lam, p, d, off)
                 for path in (1, 3, 0):
