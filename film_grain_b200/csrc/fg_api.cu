@@ -121,6 +121,7 @@ int pixelwise_device(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     const size_t in_stride = (size_t)p->in_w * p->in_h, out_stride = (size_t)p->out_w * p->out_h;
     const int band_rows = c.row_end - c.row_begin;
     uint32_t path = p->path;
+    if (p->path != FG_PATH_AUTO && p->path != FG_PATH_STAGED) FG_CUDA(ctx, flush_upload(ctx));
     if (path == FG_PATH_AUTO) {
         // The cell table costs ~ (6 / planes + 6.5) ps per Boolean-model cell of the band whatever N is (the
         // first-draw bitmap is shared by the planes); evaluating from it costs ~6 ps per sample, regenerating
@@ -132,10 +133,12 @@ int pixelwise_device(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
         const double samples_per_cell = (double)p->n_samples * (double)p->zoom * (double)p->zoom * (double)p->delta * (double)p->delta;
         path = (samples_per_cell * direct_ps < 6.0 / n_planes + 6.5) ? FG_PATH_DIRECT : FG_PATH_STAGED;
     }
+    if (path != FG_PATH_STAGED) FG_CUDA(ctx, flush_upload(ctx));
     if (path == FG_PATH_TILED || path == FG_PATH_STAGED) {
         int rc = tile_render(ctx, p, c, n_planes, d_lambda, d_offsets, d_out, path);
         if (rc != 1) return rc; // 1 = "tiled path not applicable, use direct"
     }
+    FG_CUDA(ctx, flush_upload(ctx));
     // grid.y is limited to 65 535 CTAs of 8 rows: taller bands (validate() admits 2^30 rows) go in row chunks
     const int rows_per_launch = 65535 * 8;
     for (int y = c.row_begin; y < c.row_end; y += rows_per_launch) {
@@ -372,12 +375,24 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
     static const bool poison = std::getenv("FG_B200_POISON") && std::atoi(std::getenv("FG_B200_POISON")) != 0; // tests: NaN outside the uploaded rows
     if (poison) FG_CUDA(ctx, cudaMemsetAsync(ctx->lambda.p, 0xFF, in_elems * n_planes * sizeof(float), s));
     const size_t up_off = (size_t)in_r0 * p->in_w, up_elems = (size_t)(in_r1 - in_r0) * p->in_w;
-    for (int pl = 0; pl < n_planes; ++pl)
-        FG_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lambda.p + in_elems * pl + up_off, lambda[pl] + up_off, up_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    // A whole-frame pixel-wise render of a few MB or more leaves the upload to the pipeline, which overlaps it with the
+    // thresholds and the first-draw bitmap row chunk by row chunk (fg_pixel_host.cuh); everything else uploads here.
+    static const bool chunk_env = !(std::getenv("FG_B200_CHUNKED_UPLOAD") && std::atoi(std::getenv("FG_B200_CHUNKED_UPLOAD")) == 0);
+    const bool defer = chunk_env && algo == FG_ALGO_PIXEL && in_r0 == 0 && in_r1 == (int)p->in_h && p->in_h >= 64 && ctx->copy_stream &&
+                       in_elems * n_planes * sizeof(float) >= ((size_t)4 << 20) && !ctx->tcache.enabled;
+    ctx->up.pending = false;
+    if (defer) {
+        ctx->up.pending = true;
+        ctx->up.host = lambda; ctx->up.n_planes = n_planes; ctx->up.in_w = p->in_w; ctx->up.in_h = p->in_h; ctx->up.dev = (float*)ctx->lambda.p;
+    } else {
+        for (int pl = 0; pl < n_planes; ++pl)
+            FG_CUDA(ctx, cudaMemcpyAsync((float*)ctx->lambda.p + in_elems * pl + up_off, lambda[pl] + up_off, up_elems * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
     FG_CUDA(ctx, cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)p->n_samples * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
     rc = render_planes_device_locked(ctx, p, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, d_dst);
-    if (rc) { cudaStreamSynchronize(s); return rc; }
+    ctx->up.pending = false; // (consumed by now; the caller's plane array is not referenced past this call)
+    if (rc) { cudaStreamSynchronize(s); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream); return rc; }
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
     if (cancel_armed(ctx)) { // a copy into pageable memory blocks the host until the kernels are done: watch the flag first
         FG_CUDA(ctx, wait_stream(ctx));
@@ -738,6 +753,9 @@ int fg_context_create(fg_ctx** out, int device) {
         return FG_ERR_OOM;
     }
     std::memset(ctx->h_pin, 0, 16 * sizeof(uint64_t));
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->copy_stream = nullptr; }
+    for (auto& e : ctx->up_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); e = nullptr; }
     // in-launch cancel (fg_ctx.cuh: wait_stream); without these the flag is still honoured between the stages
     if (cudaStreamCreateWithFlags(&ctx->abort_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventDisableTiming) != cudaSuccess ||
@@ -810,6 +828,8 @@ void fg_context_destroy(fg_ctx* ctx) {
         if (ctx->d_abort) cudaFree(ctx->d_abort);
         if (ctx->h_one) cudaFreeHost(ctx->h_one);
         if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+        if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+        for (auto& e : ctx->up_ev) if (e) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         cudaGetLastError();
     }

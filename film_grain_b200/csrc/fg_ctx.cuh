@@ -75,6 +75,19 @@ struct fg_ctx {
     cudaStream_t abort_stream = nullptr;
     cudaEvent_t ev_wait = nullptr;
     bool abort_sent = false;
+    // A whole-frame lambda upload the host entry point has NOT issued yet: the staged pixel-wise pipeline issues it in row
+    // chunks on `copy_stream` and runs the thresholds + first-draw bitmap of chunk k while chunk k + 1 is still crossing
+    // PCIe (or, for pageable planes, being staged by the host).  Whoever reaches the data first consumes it
+    // (flush_upload: plain copies on the main stream).
+    struct {
+        bool pending = false;
+        const float* const* host = nullptr; // the caller's planes
+        int n_planes = 0;
+        size_t in_w = 0, in_h = 0;
+        float* dev = nullptr;               // ctx->lambda
+    } up;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t up_ev[5] = {};
     TableCache tcache;
     // progressive refinement (fg_refine_planes): `acc` holds the render of samples [0, acc_k) of the geometry below
     struct { bool valid = false; uint32_t k = 0, n_planes = 0, out_w = 0, out_h = 0, row_begin = 0, row_end = 0; int algo = 0; } prog;
@@ -168,6 +181,18 @@ cudaError_t wait_stream(fg_ctx* ctx) {
         }
         std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
+}
+
+// issue a still-pending lambda upload in one piece on the main stream (every path but the chunked one below)
+cudaError_t flush_upload(fg_ctx* ctx) {
+    if (!ctx->up.pending) return cudaSuccess;
+    ctx->up.pending = false;
+    const size_t elems = ctx->up.in_w * ctx->up.in_h;
+    for (int pl = 0; pl < ctx->up.n_planes; ++pl) {
+        const cudaError_t e = cudaMemcpyAsync(ctx->up.dev + elems * pl, ctx->up.host[pl], elems * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // the per-call cancel flag lives in the context only while the call holds the context mutex

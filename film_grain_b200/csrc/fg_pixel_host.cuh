@@ -441,25 +441,72 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     const int iy0 = std::min(std::max((int)std::floor((double)g.bm_j0 * (double)p->delta) - 1, 0), (int)p->in_h - 1);
     const int iy1 = std::min(std::max((int)std::floor((double)(g.bm_j0 + g.bm_rows) * (double)p->delta) + 1, 0), (int)p->in_h - 1);
     const size_t thr_first = (size_t)iy0 * p->in_w, thr_n = (size_t)(iy1 - iy0 + 1) * p->in_w;
-    const unsigned tb = (unsigned)std::min<size_t>((thr_n + 255) / 256, (size_t)ctx->sm_count * 16);
-    if (!reuse) k_thresholds<<<dim3(tb, (unsigned)n_planes), 256, 0, s>>>(d_lambda, in_stride, thr_first, thr_n, p->delta, d_thr, d_e);
-    FG_CUDA(ctx, cudaGetLastError());
     uint32_t* d_bm = (uint32_t*)ctx->bitmap.p;
-    if (!reuse) {
-        dim3 bgrid((unsigned)((g.bm_rows + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
+    // thresholds of the input rows [r0, r1) and first-draw bits of the cell rows [c0, c1) of the rectangle
+    auto launch_front = [&](int r0, int r1, int c0, int c1) -> int {
+        if (r1 > r0) {
+            const size_t first = (size_t)r0 * p->in_w, n = (size_t)(r1 - r0) * p->in_w;
+            const unsigned tb = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sm_count * 16);
+            k_thresholds<<<dim3(tb, (unsigned)n_planes), 256, 0, s>>>(d_lambda, in_stride, first, n, p->delta, d_thr, d_e);
+            FG_CUDA(ctx, cudaGetLastError());
+            ctx->stats.launches += 1;
+        }
+        if (c1 > c0) {
+            dim3 bgrid((unsigned)((c1 - c0 + FG_BM_ROWS - 1) / FG_BM_ROWS), (g.bm_pitchw * 32u + 255u) / 256u);
 #define FG_LAUNCH_BM(SD, NPL)                                                                                       \
     k_first_draw_bitmap<SD, NPL><<<bgrid, 256, 0, s>>>(d_thr, in_stride, n_planes, d_bm, bm_plane_words, g.bm_i0, g.bm_j0, \
-                                                       g.bm_cols, g.bm_rows, g.bm_pitchw, c)
-        if (c.seeding == 0) {
-            if (n_planes == 3) FG_LAUNCH_BM(0, 3);
-            else if (n_planes == 1) FG_LAUNCH_BM(0, 1);
-            else FG_LAUNCH_BM(0, 0);
-        } else {
-            FG_LAUNCH_BM(1, 0);
-        }
+                                                       g.bm_cols, c1, g.bm_pitchw, c0, c)
+            if (c.seeding == 0) {
+                if (n_planes == 3) FG_LAUNCH_BM(0, 3);
+                else if (n_planes == 1) FG_LAUNCH_BM(0, 1);
+                else FG_LAUNCH_BM(0, 0);
+            } else {
+                FG_LAUNCH_BM(1, 0);
+            }
 #undef FG_LAUNCH_BM
-        FG_CUDA(ctx, cudaGetLastError());
-        ctx->stats.launches += 2;
+            FG_CUDA(ctx, cudaGetLastError());
+            ctx->stats.launches += 1;
+        }
+        return FG_OK;
+    };
+    if (!reuse && ctx->up.pending && staged && iy0 == 0 && iy1 == (int)p->in_h - 1 && ctx->up_ev[4]) {
+        // ---- chunked upload: lambda rows cross PCIe (or the host's staging buffer) on `copy_stream` in K row chunks; the
+        // thresholds and the first-draw bits of the cell rows that read chunk k run while chunk k + 1 is on its way.
+        // A cell row j reads the input row clamp(floor(f32(j) * delta)) (src/pixelwise.rs:69-73), non-decreasing in j.
+        ctx->up.pending = false;
+        const int K = 4, in_h = (int)p->in_h;
+        auto in_row = [&](int row) { // the kernels' own arithmetic: one f32 multiply, floor, clamp
+            const float v = std::floor((float)(g.bm_j0 + row) * p->delta);
+            const int iy = v < -2.0e9f ? INT_MIN : (v > 2.0e9f ? INT_MAX : (int)v);
+            return std::min(std::max(iy, 0), in_h - 1);
+        };
+        FG_CUDA(ctx, cudaEventRecord(ctx->up_ev[4], s)); // the copies come after whatever the main stream did to the buffer (tests: NaN fill)
+        FG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->up_ev[4], 0));
+        int c_done = 0;
+        for (int k = 0; k < K; ++k) {
+            const int r0 = (int)((long long)in_h * k / K), r1 = (int)((long long)in_h * (k + 1) / K);
+            const size_t off = (size_t)r0 * p->in_w, n = (size_t)(r1 - r0) * p->in_w;
+            for (int pl = 0; pl < n_planes && n; ++pl)
+                FG_CUDA(ctx, cudaMemcpyAsync(ctx->up.dev + in_stride * pl + off, ctx->up.host[pl] + off, n * sizeof(float), cudaMemcpyHostToDevice, ctx->copy_stream));
+            FG_CUDA(ctx, cudaEventRecord(ctx->up_ev[k], ctx->copy_stream));
+            FG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->up_ev[k], 0));
+            int c1 = g.bm_rows;
+            if (k + 1 < K) { // leading cell rows whose input row lies below r1
+                int lo = c_done, hi = g.bm_rows; // in_row(row) < r1 for row < lo; first row with in_row >= r1 is in [lo, hi]
+                while (lo < hi) {
+                    const int mid = lo + (hi - lo) / 2;
+                    if (in_row(mid) < r1) lo = mid + 1; else hi = mid;
+                }
+                c1 = lo;
+            }
+            int rcf;
+            if ((rcf = launch_front(r0, r1, c_done, c1))) return rcf;
+            c_done = c1;
+        }
+    } else {
+        FG_CUDA(ctx, flush_upload(ctx));
+        int rcf;
+        if (!reuse && (rcf = launch_front(iy0, iy1 + 1, 0, g.bm_rows))) return rcf;
     }
     CellTable tab{};
     double table_dens = 0.0;

@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(256) k_thresholds(const float* __restrict__ la
 template <int SEEDING, int NP> // compile-time seeding variant and plane count (NP = 0: run-time n_planes)
 __global__ void __launch_bounds__(256) k_first_draw_bitmap(const uint64_t* __restrict__ thr_planes, size_t in_stride,
                                                             int n_planes, uint32_t* __restrict__ bm, size_t bm_plane_words,
-                                                            int i0, int j0, int cols, int rows, uint32_t pitchw, RenderConsts c) {
+                                                            int i0, int j0, int cols, int rows, uint32_t pitchw, int row_off, RenderConsts c) {
     if (cta_aborted(c)) return;
     const int col = blockIdx.y * 256 + threadIdx.x;
-    const int row0 = blockIdx.x * FG_BM_ROWS;
+    const int row0 = row_off + blockIdx.x * FG_BM_ROWS; // rows [row_off, rows) of the rectangle (chunked upload: a slice per launch)
     const bool valid = col < cols;
     const bool store = (threadIdx.x & 31) == 0 && col < (int)(pitchw * 32u);
     const int i = i0 + col;
