@@ -390,7 +390,12 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
     }
     FG_CUDA(ctx, cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)p->n_samples * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+    static const bool slice_env = !(std::getenv("FG_B200_SLICED_OUTPUT") && std::atoi(std::getenv("FG_B200_SLICED_OUTPUT")) == 0);
+    ctx->outp.want = slice_env && !mapped && algo == FG_ALGO_PIXEL && ctx->copy_stream && !cancel_armed(ctx) &&
+                     out_elems * n_planes * sizeof(float) >= ((size_t)8 << 20);
+    ctx->outp.n = 0;
     rc = render_planes_device_locked(ctx, p, c, algo, n_planes, (const float*)ctx->lambda.p, (const float*)ctx->offsets.p, d_dst);
+    ctx->outp.want = false;
     ctx->up.pending = false; // (consumed by now; the caller's plane array is not referenced past this call)
     if (rc) { cudaStreamSynchronize(s); if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream); return rc; }
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
@@ -399,6 +404,20 @@ int render_planes_host(fg_ctx* ctx, const fg_params* p, int algo, int n_planes, 
         if (cancelled(ctx)) return set_err(ctx, FG_ERR_CANCELLED, "cancelled");
     }
     const size_t band_off = (size_t)c.row_begin * p->out_w, band_elems = (size_t)(c.row_end - c.row_begin) * p->out_w;
+    if (!mapped && ctx->outp.n > 1) { // the evaluation ran in row slices: copy slice e while slice e + 1 is being evaluated
+        int y0 = c.row_begin;
+        for (int e = 0; e < ctx->outp.n; ++e) {
+            const int y1 = ctx->outp.row_end[e];
+            FG_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->outp.ev[e], 0));
+            const size_t o = (size_t)y0 * p->out_w, n = (size_t)(y1 - y0) * p->out_w;
+            for (int pl = 0; pl < n_planes && n; ++pl)
+                FG_CUDA(ctx, cudaMemcpyAsync(out[pl] + o, (float*)ctx->out.p + out_elems * pl + o, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            y0 = y1;
+        }
+        FG_CUDA(ctx, cudaEventRecord(ctx->up_ev[4], ctx->copy_stream));
+        FG_CUDA(ctx, cudaStreamWaitEvent(s, ctx->up_ev[4], 0)); // the wait below covers the copies
+        ctx->outp.n = 0;
+    } else
     for (int pl = 0; pl < n_planes && !mapped; ++pl) // mapped: the kernels' own stores were the transfer
         FG_CUDA(ctx, cudaMemcpyAsync(out[pl] + band_off, (float*)ctx->out.p + out_elems * pl + band_off, band_elems * sizeof(float), cudaMemcpyDeviceToHost, s));
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
@@ -756,6 +775,8 @@ int fg_context_create(fg_ctx** out, int device) {
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); ctx->copy_stream = nullptr; }
     for (auto& e : ctx->up_ev)
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); e = nullptr; }
+    for (auto& e : ctx->outp.ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); e = nullptr; }
     // in-launch cancel (fg_ctx.cuh: wait_stream); without these the flag is still honoured between the stages
     if (cudaStreamCreateWithFlags(&ctx->abort_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_wait, cudaEventDisableTiming) != cudaSuccess ||
@@ -830,6 +851,7 @@ void fg_context_destroy(fg_ctx* ctx) {
         if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
         if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
         for (auto& e : ctx->up_ev) if (e) cudaEventDestroy(e);
+        for (auto& e : ctx->outp.ev) if (e) cudaEventDestroy(e);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         cudaGetLastError();
     }

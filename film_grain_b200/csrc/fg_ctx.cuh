@@ -86,6 +86,14 @@ struct fg_ctx {
         size_t in_w = 0, in_h = 0;
         float* dev = nullptr;               // ctx->lambda
     } up;
+    // Pageable output planes: the pipeline evaluates the band in row slices and records an event after each, the host
+    // entry point copies slice e on `copy_stream` while slice e + 1 is being evaluated.
+    struct {
+        bool want = false;
+        int n = 0;
+        int row_end[4] = {};
+        cudaEvent_t ev[4] = {};
+    } outp;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t up_ev[5] = {};
     TableCache tcache;

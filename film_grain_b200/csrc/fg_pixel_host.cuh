@@ -584,70 +584,106 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
     }
     const float2* off = (const float2*)d_offsets;
     FG_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-    SkewPlan sk{};
-    TriPlan tr{};
-    if (staged && skew_ok) tr = tri_plan(ctx, p, c, n_planes, table_dens);
-    if (staged && skew_ok && !tr.ok) sk = skew_plan(ctx, p, c, n_planes, table_dens);
-    uint32_t units_run = units;
-    if (tr.ok) {
-        TriCfg& k = tr.cfg;
-        k.bm_i0 = g.bm_i0; k.bm_j0 = g.bm_j0; k.bm_cols = g.bm_cols; k.bm_rows = g.bm_rows; k.ppitch = g.ppitch; k.r2c = g.r2c;
-        units_run = (uint32_t)k.n_strips * k.n_segs * n_planes;
-        if (units_run > units) { // the list was sized for the strip kernel's segments
-            if ((rc = ensure(ctx, ctx->tiles, (size_t)units_run * sizeof(TileRef) + 64))) return rc;
+    // ---- evaluation of the rows [cb.row_begin, cb.row_end) of the band from its table: plan, launch, fallback list ----
+    auto eval_rows = [&](const RenderConsts& cb, bool whole) -> int {
+        TilePlan plc = pl;
+        if (!whole) {
+            plc = tile_plan(ctx, p, cb, n_planes, staged);
+            if (!plc.ok) return 1;
+        }
+        TileCfg gc = plc.cfg;
+        gc.bm_i0 = g.bm_i0; gc.bm_j0 = g.bm_j0; gc.bm_cols = g.bm_cols; gc.bm_rows = g.bm_rows; gc.bm_pitchw = g.bm_pitchw; gc.ppitch = g.ppitch; gc.r2c = g.r2c;
+        const uint32_t units_c = (uint32_t)gc.n_strips * gc.n_segs * n_planes;
+        if (!whole) {
+            if ((rc = ensure(ctx, ctx->tiles, (size_t)units_c * sizeof(TileRef) + 64))) return rc;
             d_fbcount = (uint32_t*)ctx->tiles.p;
             d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
-            FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+            FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s)); // every slice starts an empty fallback list
         }
-        k_pixelwise_tri<FG_TRI_SPW_C><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
-        g.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
-    } else if (sk.ok) {
-        SkewCfg& k = sk.cfg;
-        k.bm_i0 = g.bm_i0; k.bm_j0 = g.bm_j0; k.bm_cols = g.bm_cols; k.bm_rows = g.bm_rows; k.ppitch = g.ppitch; k.r2c = g.r2c;
-        units_run = (uint32_t)k.n_strips * k.n_segs * n_planes;
-        if (units_run > units) { // the list was sized for the strip kernel's segments
-            if ((rc = ensure(ctx, ctx->tiles, (size_t)units_run * sizeof(TileRef) + 64))) return rc;
-            d_fbcount = (uint32_t*)ctx->tiles.p;
-            d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
-            FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+        SkewPlan sk{};
+        TriPlan tr{};
+        if (staged && skew_ok) tr = tri_plan(ctx, p, cb, n_planes, table_dens);
+        if (staged && skew_ok && !tr.ok) sk = skew_plan(ctx, p, cb, n_planes, table_dens);
+        uint32_t units_run = units_c;
+        if (tr.ok) {
+            TriCfg& k = tr.cfg;
+            k.bm_i0 = gc.bm_i0; k.bm_j0 = gc.bm_j0; k.bm_cols = gc.bm_cols; k.bm_rows = gc.bm_rows; k.ppitch = gc.ppitch; k.r2c = gc.r2c;
+            units_run = (uint32_t)k.n_strips * k.n_segs * n_planes;
+            if (units_run > units_c) { // the list was sized for the strip kernel's segments
+                if ((rc = ensure(ctx, ctx->tiles, (size_t)units_run * sizeof(TileRef) + 64))) return rc;
+                d_fbcount = (uint32_t*)ctx->tiles.p;
+                d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
+                FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+            }
+            k_pixelwise_tri<FG_TRI_SPW_C><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, cb, tab);
+            gc.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
+        } else if (sk.ok) {
+            SkewCfg& k = sk.cfg;
+            k.bm_i0 = gc.bm_i0; k.bm_j0 = gc.bm_j0; k.bm_cols = gc.bm_cols; k.bm_rows = gc.bm_rows; k.ppitch = gc.ppitch; k.r2c = gc.r2c;
+            units_run = (uint32_t)k.n_strips * k.n_segs * n_planes;
+            if (units_run > units_c) { // the list was sized for the strip kernel's segments
+                if ((rc = ensure(ctx, ctx->tiles, (size_t)units_run * sizeof(TileRef) + 64))) return rc;
+                d_fbcount = (uint32_t*)ctx->tiles.p;
+                d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
+                FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
+            }
+            if (sk.spwc == 4) k_pixelwise_skew<4><<<units_run, FG_SK_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, cb, tab);
+            else k_pixelwise_skew<8><<<units_run, FG_SK_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, cb, tab);
+            gc.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
+        } else if (staged) {
+            if (cb.rad.lognorm) launch_strip<true, true>(plc.spwc, units_c, gc.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_c, gc, cb, tab);
+            else launch_strip<false, true>(plc.spwc, units_c, gc.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_c, gc, cb, tab);
+        } else {
+            if (cb.rad.lognorm) launch_strip<true, false>(plc.spwc, units_c, gc.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_c, gc, cb, tab);
+            else launch_strip<false, false>(plc.spwc, units_c, gc.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_c, gc, cb, tab);
         }
-        if (sk.spwc == 4) k_pixelwise_skew<4><<<units_run, FG_SK_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
-        else k_pixelwise_skew<8><<<units_run, FG_SK_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, c, tab);
-        g.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
-    } else if (staged) {
-        if (c.rad.lognorm) launch_strip<true, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
-        else launch_strip<false, true>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
-    } else {
-        if (c.rad.lognorm) launch_strip<true, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
-        else launch_strip<false, false>(pl.spwc, units, g.total, s, d_bm, bm_plane_words, d_e, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units, g, c, tab);
+        FG_CUDA(ctx, cudaGetLastError());
+        FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
+        const uint32_t chunks = (uint32_t)((gc.SEG + 7) / 8);
+        const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units_run * chunks, (uint64_t)ctx->sm_count * 8);
+        if (staged && cb.rad.lognorm)
+            k_pixelwise_table_tiles<true><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
+                                                              chunks, d_fbtotal, gc, cb, tab);
+        else if (staged)
+            k_pixelwise_table_tiles<false><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
+                                                               chunks, d_fbtotal, gc, cb, tab);
+        else
+            k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
+                                                         chunks, d_fbtotal, cb);
+        FG_CUDA(ctx, cudaGetLastError());
+        ctx->stats.launches += 2;
+        if (std::getenv("FG_B200_DEBUG"))
+            std::fprintf(stderr, "[fg] band %d..%d staged=%d TH=%d SEG=%d RH=%d CWB=%d GCAP=%d smem=%u units_c=%u\n", cb.row_begin, cb.row_end,
+                         (int)staged, gc.TH, gc.SEG, gc.RH, gc.CWB, gc.GCAP, gc.total, units_c);
+        ctx->stats.tiles_total += units_run;
+        ctx->strip_launches += 1;
+        ctx->eval_kernel = tr.ok ? "k_pixelwise_tri" : (sk.ok ? "k_pixelwise_skew" : "k_pixelwise_strip");
+        if (std::getenv("FG_B200_DEBUG") && tr.ok)
+            std::fprintf(stderr, "[fg] tri m=%d D=%d AMAX=%d NQ=%d PS=%d MCAP=%d GS=%d RH=%d NB=%d SEG=%d segs=%d smem=%u dens=%.3f\n", tr.cfg.m, tr.cfg.D, tr.cfg.AMAX,
+                         tr.cfg.NQ, tr.cfg.PS, tr.cfg.MCAP, tr.cfg.GS, tr.cfg.RH, tr.cfg.NB, tr.cfg.SEG, tr.cfg.n_segs, tr.cfg.total, table_dens);
+        if (std::getenv("FG_B200_DEBUG") && sk.ok)
+            std::fprintf(stderr, "[fg] skew D=%d PS=%d MCAP=%d TCAP=%d R=%d SEG=%d segs=%d smem=%u dens=%.3f\n", sk.cfg.D, sk.cfg.PS, sk.cfg.MCAP, sk.cfg.TCAP, sk.cfg.R,
+                         sk.cfg.SEG, sk.cfg.n_segs, sk.cfg.total, table_dens);
+        return FG_OK;
+    };
+    // A host caller with pageable output planes (fg_ctx::outp.want) gets the band evaluated in three row slices, each
+    // followed by an event: the device->host copy of slice e runs under the evaluation of slice e + 1
+    // (render_planes_host).  The table is the band's; only the evaluation launch is sliced.
+    const int band_rows = c.row_end - c.row_begin;
+    const int E = (ctx->outp.want && staged && band_rows >= 768 && ctx->outp.ev[0]) ? 3 : 1;
+    ctx->outp.n = 0;
+    for (int e = 0; e < E; ++e) {
+        RenderConsts cb = c;
+        cb.row_begin = c.row_begin + (int)((long long)band_rows * e / E);
+        cb.row_end = c.row_begin + (int)((long long)band_rows * (e + 1) / E);
+        const int rce = eval_rows(cb, E == 1);
+        if (rce) { ctx->outp.n = 0; return rce; } // whoever renders the band instead writes it after the slice events
+        if (E > 1) {
+            FG_CUDA(ctx, cudaEventRecord(ctx->outp.ev[e], s));
+            ctx->outp.row_end[e] = cb.row_end;
+            ctx->outp.n = e + 1;
+        }
     }
-    FG_CUDA(ctx, cudaGetLastError());
-    FG_CUDA(ctx, cudaEventRecord(ctx->ev[5], s));
-    const uint32_t chunks = (uint32_t)((g.SEG + 7) / 8);
-    const unsigned fbb = (unsigned)std::min<uint64_t>((uint64_t)units_run * chunks, (uint64_t)ctx->sm_count * 8);
-    if (staged && c.rad.lognorm)
-        k_pixelwise_table_tiles<true><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
-                                                          chunks, d_fbtotal, g, c, tab);
-    else if (staged)
-        k_pixelwise_table_tiles<false><<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
-                                                           chunks, d_fbtotal, g, c, tab);
-    else
-        k_pixelwise_direct_tiles<<<fbb, 256, 0, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run,
-                                                     chunks, d_fbtotal, c);
-    FG_CUDA(ctx, cudaGetLastError());
-    ctx->stats.launches += 2;
-    if (std::getenv("FG_B200_DEBUG"))
-        std::fprintf(stderr, "[fg] band %d..%d staged=%d TH=%d SEG=%d RH=%d CWB=%d GCAP=%d smem=%u units=%u\n", c.row_begin, c.row_end,
-                     (int)staged, g.TH, g.SEG, g.RH, g.CWB, g.GCAP, g.total, units);
-    ctx->stats.tiles_total += units_run;
-    ctx->strip_launches += 1;
-    ctx->eval_kernel = tr.ok ? "k_pixelwise_tri" : (sk.ok ? "k_pixelwise_skew" : "k_pixelwise_strip");
-    if (std::getenv("FG_B200_DEBUG") && tr.ok)
-        std::fprintf(stderr, "[fg] tri m=%d D=%d AMAX=%d NQ=%d PS=%d MCAP=%d GS=%d RH=%d NB=%d SEG=%d segs=%d smem=%u dens=%.3f\n", tr.cfg.m, tr.cfg.D, tr.cfg.AMAX,
-                     tr.cfg.NQ, tr.cfg.PS, tr.cfg.MCAP, tr.cfg.GS, tr.cfg.RH, tr.cfg.NB, tr.cfg.SEG, tr.cfg.n_segs, tr.cfg.total, table_dens);
-    if (std::getenv("FG_B200_DEBUG") && sk.ok)
-        std::fprintf(stderr, "[fg] skew D=%d PS=%d MCAP=%d TCAP=%d R=%d SEG=%d segs=%d smem=%u dens=%.3f\n", sk.cfg.D, sk.cfg.PS, sk.cfg.MCAP, sk.cfg.TCAP, sk.cfg.R,
-                     sk.cfg.SEG, sk.cfg.n_segs, sk.cfg.total, table_dens);
     return FG_OK;
 }
 
@@ -667,6 +703,8 @@ int tile_render(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int n_pl
     if (rc == 2 || rc == 3) {
         // 2: the whole band does not fit one table -> row sub-bands; whatever cannot be staged (and
         // 3: a table overflow) is rendered with in-kernel generation
+        ctx->outp.want = false; // several bands: one copy of the whole result after the last one
+        ctx->outp.n = 0;
         const int band = c.row_end - c.row_begin;
         int done = c.row_begin;
         for (int parts = 2; rc == 2 && parts <= 64 && done == c.row_begin; parts *= 2) {
