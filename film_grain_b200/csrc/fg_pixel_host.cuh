@@ -206,18 +206,26 @@ TriPlan tri_plan(const fg_ctx* ctx, const fg_params* p, const RenderConsts& c, i
     TriPlan pl{};
     pl.ok = false;
     static const bool enabled = !(std::getenv("FG_B200_TRI") && std::atoi(std::getenv("FG_B200_TRI")) == 0);
-    // Measured on a B200: 33 ms against 36 ms for k_pixelwise_strip at C2 (N = 256), but 144 ms against 86 ms at C4 (N = 64:
-    // four samples per evaluation warp do not cover the loader's per-step latency chain) -- the kernel is used for N > 128.
-    if (!enabled || c.rad.lognorm || p->rm != p->delta || p->n_samples > (uint32_t)FG_TRI_SPW_C * FG_TRI_WARPS || p->n_samples <= (uint32_t)FG_TRI_SPW_B * FG_TRI_WARPS) return pl;
+    // Measured on a B200 (profiles/README.md).  128 < N <= 256: 28 ms against 36 ms for k_pixelwise_strip at C2.  N <= 128: the
+    // kernel's time hardly depends on N (its loader warps set the step period: ~26 ms for a 4K RGB frame at 10 cell rows per
+    // output row) while the strip kernel's does, so it only pays where a step needs few cell rows: cpr = 1 / (zoom * delta)
+    // <= 5 (zoom 2 at r = 0.1, zoom 4 at r = 0.05 = C4: 74 ms against 88 ms; zoom 4 at r = 0.1: 5.5 against 10.8 ms) and
+    // N > 32 (a quarter-filled warp of samples is the strip kernel's territory).  FG_B200_TRI_SMALLN = 0 / 1 forces it.
+    if (!enabled || c.rad.lognorm || p->rm != p->delta || p->n_samples > (uint32_t)FG_TRI_SPW_C * FG_TRI_WARPS) return pl;
     const double inv_zoom = 1.0 / (double)p->zoom, delta = p->delta, rm = p->rm;
+    const double cpr = inv_zoom / delta; // cell rows per output pixel row
+    if (p->n_samples <= (uint32_t)FG_TRI_SPW_B * FG_TRI_WARPS) {
+        const char* sn = std::getenv("FG_B200_TRI_SMALLN"); // read per call: tests and tools switch it
+        const bool small_n = sn ? std::atoi(sn) != 0 : (p->n_samples > 32u && cpr <= 5.01);
+        if (!small_n) return pl;
+    }
     const double ox = (double)c.off_max_x - (double)c.off_min_x;
     const double cwb = (31.0 * inv_zoom + ox + 2.0 * rm) / delta + 4.0 + 3.0; // + alignment shift
     if (!(cwb < 2000.0)) return pl;
     const int CWB = (int)cwb;
     const int PS = (CWB + 1 + 7) / 8 * 8;
-    const double cpr = inv_zoom / delta; // cell rows per output pixel row
     if (!(cpr > 0.05 && cpr < 24.0)) return pl;
-    const int spw = FG_TRI_SPW_C;
+    const int spw = p->n_samples <= (uint32_t)FG_TRI_SPW_A * FG_TRI_WARPS ? FG_TRI_SPW_A : (p->n_samples <= (uint32_t)FG_TRI_SPW_B * FG_TRI_WARPS ? FG_TRI_SPW_B : FG_TRI_SPW_C);
     const int band = c.row_end - c.row_begin;
     const int skrange = (int)std::nearbyint((double)c.off_max_y * (double)p->zoom) - (int)std::nearbyint((double)c.off_min_y * (double)p->zoom);
     if (skrange < 0 || skrange > 200) return pl;
@@ -336,7 +344,9 @@ int tile_setup(fg_ctx* ctx) {
     if ((e = cudaFuncSetAttribute(k_pixelwise_skew<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
         (e = cudaFuncSetAttribute(k_pixelwise_skew<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_skew)");
-    if ((e = cudaFuncSetAttribute(k_pixelwise_tri<FG_TRI_SPW_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
+    if ((e = cudaFuncSetAttribute(k_pixelwise_tri<FG_TRI_SPW_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_tri<FG_TRI_SPW_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(k_pixelwise_tri<FG_TRI_SPW_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess)
         return map_cuda_error(ctx, e, "cudaFuncSetAttribute(k_pixelwise_tri)");
     return FG_OK;
 }
@@ -615,7 +625,9 @@ int tile_render_band(fg_ctx* ctx, const fg_params* p, const RenderConsts& c, int
                 d_fblist = (TileRef*)((unsigned char*)ctx->tiles.p + 64);
                 FG_CUDA(ctx, cudaMemsetAsync(d_fbcount, 0, 64, s));
             }
-            k_pixelwise_tri<FG_TRI_SPW_C><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, cb, tab);
+            if (tr.spw == FG_TRI_SPW_A) k_pixelwise_tri<FG_TRI_SPW_A><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, cb, tab);
+            else if (tr.spw == FG_TRI_SPW_B) k_pixelwise_tri<FG_TRI_SPW_B><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, cb, tab);
+            else k_pixelwise_tri<FG_TRI_SPW_C><<<units_run, FG_TRI_THREADS, k.total, s>>>(d_lambda, in_stride, off, d_out, out_stride, d_fblist, d_fbcount, units_run, k, cb, tab);
             gc.SEG = k.SEG; // the fallback kernel chunks a listed tile by this height
         } else if (sk.ok) {
             SkewCfg& k = sk.cfg;

@@ -40,7 +40,7 @@ namespace fg {
 #define FG_TRI_EWARPS 16 // evaluation warps (24 measured slower at C2: 72 registers per thread spill in the test loop)
 #endif
 #ifndef FG_TRI_DWARPS
-#define FG_TRI_DWARPS 3  // loader / merge / output warps (4 measured slower at C2: they take issue slots from the evaluation warps)
+#define FG_TRI_DWARPS 4  // loader / merge / output warps: loader warp 0 (placement + its share of the merge) sets the step period; 3: 29.6 ms, 4: 28.2 ms, 5 / 6: 32.2 / 32.6 ms (registers) at C2
 #endif
 #define FG_TRI_WARPS FG_TRI_EWARPS // samples are dealt over the evaluation warps: k = s * FG_TRI_WARPS + warp
 #define FG_TRI_THREADS ((FG_TRI_EWARPS + FG_TRI_DWARPS) * 32)

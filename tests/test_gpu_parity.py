@@ -127,6 +127,11 @@ TRI_CASES = [
     # dense content: groups of cell rows that do not fit the merged ring are skipped and their samples walk the cell table
     ("tri_dense_gradient", 96, 64, dict(radius=0.1, n_samples=256), "gradient"),
     ("tri_saturated_block", 96, 80, dict(radius=0.1, n_samples=160), "saturated"),
+    # N <= 128: the 4- and 8-samples-per-warp instances, chosen by the planner where a step needs few cell rows (cpr <= 5)
+    ("tri_N64_zoom2", 60, 44, dict(radius=0.1, n_samples=64, zoom=2.0), "noise"),
+    ("tri_N100_zoom4_r0.05", 40, 30, dict(radius=0.05, n_samples=100, zoom=4.0), "noise"),
+    ("tri_N33_r0.2", 90, 70, dict(radius=0.2, n_samples=33), "gradient"),
+    ("tri_N128_zoom2.5_saturated", 64, 50, dict(radius=0.1, n_samples=128, zoom=2.5), "saturated"),
 ]
 
 
@@ -140,7 +145,7 @@ def test_tri_kernel_matches_oracle(ctx, monkeypatch, name, w, h, kw, content):
     d, off, off_in = O.derive_common(p, w, h)
     img = gradient_u8(w, h) if content == "gradient" else noise_u8(w, h, seed=23)
     if content == "saturated":
-        img[20:60, 30:, :] = 255
+        img[20:min(60, h - 4), 30:, :] = 255
     lam = lambda_from_u8(img[:, :, 0], d.inv_e_pi_r2)
     ref = O.render_pixelwise(lam, p, d, off_in)
     got = ctx.render_pixelwise(fg_params_from(p, d, path=3), lam, off_in)
