@@ -26,9 +26,11 @@
 //   * Coverage bits: one ballot word per (row, sample) in a ring; a finished row is transposed (32 x 32 bit
 //     transposes through shuffles), popcounted and written as count * (1/N).
 //
-// Samples that do not visit exactly three cell rows, or start outside the step's window (f32 rounding of
-// (y -/+ rm) / delta), are evaluated from the HBM table like k_pixelwise_table_tiles does; a segment whose merged window
-// does not fit shared memory (dense content) goes to the fallback list.  Results are bit-identical to
+// Samples that visit FOUR cell rows (f32 rounding of (y -/+ rm) / delta: 0.4% of the items from y = 2048 on) are served
+// from two merged triples; those with any other row count, or that start outside the step's window, are evaluated from
+// the HBM table like k_pixelwise_table_tiles does; a segment whose merged window does not fit shared memory (dense
+// content) goes to the fallback list.  Instances: 16 samples per evaluation warp (128 < N <= 256) and, where a step
+// needs at most five cell rows per output row, 4 and 8 (32 < N <= 128); the planner (fg_pixel_host.cuh: tri_plan) chooses.  Results are bit-identical to
 // k_pixelwise_strip / k_pixelwise_direct / the oracle: the visited cell set, the f32 operations of the distance test
 // and the count are the reference's; only the order of the (commutative) "any grain covers" changes.
 #pragma once
